@@ -1,0 +1,711 @@
+// sse_kernels.cuh — device side of the B200 SSE sweep backend (sm_100a).
+//
+// One WARP advances one walker through  diagonal update + vertex-record build (K1K2)  ->  worm update (K3)
+// ->  commit + estimators (K4C)  for many sweeps inside one persistent launch; walkers never synchronise
+// with each other.  Per-walker data lives in HBM in SoA form:
+//
+//   ops  [W][M_cap]  u32   padded operator string.  "committed" mode: 0 = identity, else the op code
+//                          (bit0 = 1, bit1 = diagonal, bits 2..13 = global vertex id, bits 14.. = bond);
+//                          "indexed" mode (between K1K2 and K4C): non-identity slots hold k+1, the index of
+//                          their vertex record, so a worm start needs ONE dependent load.
+//   rec  [W][n_cap]  16 B  vertex records {op code, 4 x 24-bit links (k' << 2 | leg')}: ONE 16-byte load per
+//                          worm visit returns the operator and all four leg links (one 32 B DRAM sector), the
+//                          visit's only store goes back into the same sector.
+//   state[W][N] u8, vfirst/vlast [W][N] u32 (link of the first / last leg on each site's world line).
+//
+// The (<16 KB) vertex tables are staged in shared memory once per CTA.  Warp primitives do the scans:
+// ballot/popc prefix sums give each slot its random-stream offset (2/1/0 draws by pre-update slot type) and
+// its compact record index; shuffles resolve same-site ordering inside a 32-slot chunk.
+//
+// Every phase reproduces the reference's draw ORDER and its Float64 expressions
+// (no FMA contraction: compile with -fmad=false), so results are bit-identical to the CPU oracle under
+// the same random stream.  Reference lines are cited at each phase.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/sse_b200.h"
+#include "../../include/sse_rng.h"
+
+namespace sse {
+
+constexpr uint32_t FULL = 0xffffffffu;
+constexpr uint32_t NONE32 = 0xffffffffu;
+constexpr uint32_t NONE24 = 0x00ffffffu;
+constexpr int VBITS = 12;                 // global vertex id bits in the device op code
+constexpr uint32_t VMASK = ((1u << VBITS) - 1u) << 2;  // bits 2..13
+constexpr int BOND_SHIFT = 2 + VBITS;     // 14
+constexpr int WARPS_PER_CTA = 4;
+
+__host__ __device__ __forceinline__ uint32_t op_pack(uint32_t bond, uint32_t gv, uint32_t diag) {
+    return 1u | (diag << 1) | (gv << 2) | (bond << BOND_SHIFT);
+}
+__host__ __device__ __forceinline__ uint32_t op_gv(uint32_t op) { return (op >> 2) & ((1u << VBITS) - 1u); }
+__host__ __device__ __forceinline__ uint32_t op_bond(uint32_t op) { return op >> BOND_SHIFT; }
+
+// Shared-memory image of the vertex tables (built once on the host, copied per CTA).
+struct TabLayout {
+    int bytes;
+    int off_outc;     // uint4  [n_outcomes] {cumprob lo, cumprob hi, packed step, 0}
+    int off_weights;  // double [nv]
+    int off_trans;    // u32    [nv*max_worm*4]  (offset << 10) | count, NONE32 = invalid
+    int off_vinfo;    // u32    [nv]  leg states packed, 8 bits per leg
+    int off_diagv;    // u16    [n_diag]  global vertex id + 1, 0 = invalid
+    int off_vneg;     // u8     [nv]  1 if the vertex sign is negative
+};
+// outcome.z: bit0 = diagonal flag of the target, bits 1..12 = target gv, bits 13..14 = exit leg,
+//            bits 15..22 = exit worm, bits 23..30 = dim of the exit leg's site
+struct SmTab {
+    const uint4 *outc;
+    const double *weights;
+    const uint32_t *trans;
+    const uint32_t *vinfo;
+    const uint16_t *diagv;
+    const uint8_t *vneg;
+};
+
+struct DevModel {
+    int n_sites, n_bonds, nv, max_worm, n_est, est_max_dim, norm_sites;
+    double energy_offset;
+    const uint4 *bond_info;   // [n_bonds] {site_a | dim_a << 24, site_b | dim_b << 24, diag table base, type}
+    const uint8_t *site_dim;  // [n_sites]
+    const double *est_values; // [n_est][n_sites][est_max_dim]
+    const uint8_t *tab_blob;  // TabLayout image
+    TabLayout tl;
+};
+
+struct DevWalkers {
+    int W;
+    int64_t M_cap, n_cap;
+    uint32_t *ops;
+    uint4 *rec;
+    uint8_t *state;
+    uint32_t *vfirst, *vlast;
+    double *T;
+    int *M, *n;
+    double *num_worms, *avg_wl, *last_wlf;
+    unsigned long long *draws;
+    uint32_t *flags;
+    double *acc;                 // [W][n_obs]
+    long long *acc_cnt;          // [W][2]
+    unsigned long long *counters;// [4] visits, walker-sweeps, sum n, sum M
+    long long *dbg_len;          // [W] worm length of the last sse_dbg_worm_traverse
+    double *obs_out;             // [W][n_obs] scratch for sse_measure
+    const unsigned long long *inj;
+    long long inj_len;
+    unsigned long long seed, wid_off;
+    double twlf, atten;
+    int n_obs;
+};
+
+enum Mode : int {
+    MODE_SWEEP = 0, MODE_INIT, MODE_DIAG, MODE_MAKE_VL, MODE_WORM_UPDATE, MODE_WORM_TRAVERSE, MODE_COMMIT, MODE_MEASURE
+};
+
+struct LaunchArgs {
+    int mode, n_sweeps, thermalized, measure, warmup;
+    int l0, w0;       // MODE_WORM_TRAVERSE (0-based leg, 1-based worm)
+    long long p0;     // 0-based slot
+    int indexed;      // MODE_MEASURE: string currently in indexed mode?
+};
+
+// per-walker context held in registers (uniform across the warp)
+struct Ctx {
+    uint32_t *ops;
+    uint4 *rec;
+    uint8_t *state;
+    uint32_t *vfirst, *vlast;
+    const unsigned long long *inj;
+    long long inj_len;
+    unsigned long long seed, wid, draws;
+    double T, num_worms, avg_wl, last_wlf;
+    int M, n;
+    uint32_t flags, lane;
+    unsigned long long visits;
+};
+
+__device__ __forceinline__ uint32_t lanemask_lt() {
+    uint32_t m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+
+template <bool INJ>
+__device__ __forceinline__ uint64_t draw(const Ctx &c, unsigned long long k) {
+    if (INJ) return (long long)k < c.inj_len ? (uint64_t)__ldg(c.inj + k) : 0ull;
+    return sse_philox_draw(c.seed, c.wid, k);
+}
+
+// link j (24 bits) of a record: bits [24j, 24j+24) of the 96-bit little-endian field (y, z, w)
+__device__ __forceinline__ uint32_t rec_link(const uint4 &r, uint32_t j) {
+    uint32_t lo = (j < 2) ? r.y : ((j == 2) ? r.z : r.w);
+    uint32_t hi = (j < 2) ? r.z : r.w;
+    return __funnelshift_r(lo, hi, (24u * j) & 31u) & NONE24;
+}
+__device__ __forceinline__ uint4 rec_pack(uint32_t op, uint32_t l0, uint32_t l1, uint32_t l2, uint32_t l3) {
+    uint4 r;
+    r.x = op;
+    r.y = l0 | (l1 << 24);
+    r.z = (l1 >> 8) | (l2 << 16);
+    r.w = (l2 >> 16) | (l3 << 8);
+    return r;
+}
+// overwrite link `leg` of record `k` (3 bytes at byte 4 + 3*leg)
+__device__ __forceinline__ void rec_patch(uint4 *rec, uint32_t target_link, uint32_t value) {
+    uint8_t *b = reinterpret_cast<uint8_t *>(rec + (target_link >> 2)) + 4 + 3 * (target_link & 3u);
+    b[0] = (uint8_t)value;
+    b[1] = (uint8_t)(value >> 8);
+    b[2] = (uint8_t)(value >> 16);
+}
+
+__device__ __forceinline__ double shfl_f64(double v, int src) {
+    int lo = __double2loint(v), hi = __double2hiint(v);
+    lo = __shfl_sync(FULL, lo, src);
+    hi = __shfl_sync(FULL, hi, src);
+    return __hiloint2double(hi, lo);
+}
+__device__ __forceinline__ double shfl_up_f64(double v, int d) {
+    int lo = __double2loint(v), hi = __double2hiint(v);
+    lo = __shfl_up_sync(FULL, lo, d);
+    hi = __shfl_up_sync(FULL, hi, d);
+    return __hiloint2double(hi, lo);
+}
+__device__ __forceinline__ double warp_sum_f64(double v) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        int lo = __double2loint(v), hi = __double2hiint(v);
+        lo = __shfl_xor_sync(FULL, lo, d);
+        hi = __shfl_xor_sync(FULL, hi, d);
+        v += __hiloint2double(hi, lo);
+    }
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// K1K2: diagonal_update (src/sse.jl:137-191) fused with make_vertex_list! (src/vertex_list.jl:15-54).
+// do_diag = false builds the records of the unchanged string (make_vertex_list! alone);
+// build = false performs the diagonal update only (Carlo.init! warm-up sweeps, src/sse.jl:54-57).
+// Input string: committed mode.  Output: indexed mode if build, else committed.
+// ------------------------------------------------------------------------------------------------------
+template <bool INJ>
+__device__ void phase_diag_build(const SmTab &st, const DevModel &dm, const DevWalkers &dw, Ctx &c, bool do_diag,
+                                 bool build) {
+    const uint32_t lane = c.lane, lt = lanemask_lt();
+    const int N = dm.n_sites;
+    if (do_diag && 2ll * (long long)c.n >= (long long)c.M) {  // n >= 0.5*M  (sse.jl:138)
+        long long newM = (3ll * (long long)c.M) / 2 + 100;     // floor(1.5*M + 100) (sse.jl:143)
+        if (newM > dw.M_cap) { c.flags |= SSE_FLAG_M_OVERFLOW; return; }
+        c.M = (int)newM;  // slots beyond the old M are identity by invariant (sse.jl:144)
+    }
+    if (build) {
+        for (int s = lane; s < N; s += 32) { c.vfirst[s] = NONE32; c.vlast[s] = NONE32; }
+        __syncwarp();
+    }
+    const int M = c.M;
+    const uint32_t Nb = (uint32_t)dm.n_bonds;
+    const double p_make_bond_raw = (double)dm.n_bonds / c.T;   // sse.jl:147
+    const double p_remove_bond_raw = c.T / (double)dm.n_bonds; // sse.jl:148
+    int n = c.n;
+    uint32_t kbase = 0;
+    unsigned long long draws = c.draws;
+    const int nchunks = (M + 31) >> 5;
+
+    for (int ch = 0; ch < nchunks; ++ch) {
+        const int p = ch * 32 + (int)lane;
+        const bool active = p < M;
+        const uint32_t op = active ? c.ops[p] : 0u;
+        const bool nonid = op != 0u;
+        const bool is_id = active && !nonid;
+        const bool is_dg = nonid && (op & 2u);
+        const bool is_off = nonid && !(op & 2u);
+        uint32_t bond = op_bond(op);
+        const uint32_t gv = op_gv(op);
+        uint32_t newop = op;
+        double r = 0.0;
+
+        if (do_diag) {
+            // stream offsets: 2 draws per identity slot, 1 per diagonal operator, in slot order (Appendix A)
+            const uint32_t idm = __ballot_sync(FULL, is_id), dgm = __ballot_sync(FULL, is_dg);
+            const unsigned long long my = draws + 2u * __popc(idm & lt) + __popc(dgm & lt);
+            if (is_id) {
+                bond = (uint32_t)sse_uint_below(draw<INJ>(c, my), Nb);  // rand(rng, 1:N_b) - 1 (sse.jl:152)
+                r = sse_u01(draw<INJ>(c, my + 1));                      // sse.jl:166
+            } else if (is_dg) {
+                r = sse_u01(draw<INJ>(c, my));                          // sse.jl:178
+            }
+            draws += 2u * __popc(idm) + __popc(dgm);
+        }
+        uint4 bi = make_uint4(0, 0, 0, 0);
+        if (is_id || nonid) bi = __ldg(dm.bond_info + bond);
+        const uint32_t sa = bi.x & NONE24, sb = bi.y & NONE24;
+
+        if (do_diag) {
+            // state seen by each identity slot = state at chunk start overridden by earlier off-diagonal
+            // operators of this chunk (sse.jl:182-188)
+            const uint32_t offm = __ballot_sync(FULL, is_off);
+            uint32_t s_a = 1, s_b = 1, ta = 0, tb = 0;
+            if (is_id) { s_a = c.state[sa]; s_b = c.state[sb]; }
+            if (is_off) { const uint32_t vi = st.vinfo[gv]; ta = (vi >> 16) & 0xffu; tb = vi >> 24; }
+            bool wa = is_off, wb = is_off;
+            __syncwarp();
+            for (uint32_t m = offm; m;) {
+                const int L = __ffs(m) - 1;
+                m &= m - 1;
+                const uint32_t qa = __shfl_sync(FULL, sa, L), qb = __shfl_sync(FULL, sb, L);
+                const uint32_t qta = __shfl_sync(FULL, ta, L), qtb = __shfl_sync(FULL, tb, L);
+                if (is_id && (int)lane > L) {
+                    if (sa == qa) s_a = qta;
+                    if (sa == qb) s_a = qtb;
+                    if (sb == qa) s_b = qta;
+                    if (sb == qb) s_b = qtb;
+                }
+                if (is_off && (int)lane < L) {  // a later operator of the chunk overwrites this site
+                    if (sa == qa || sa == qb) wa = false;
+                    if (sb == qa || sb == qb) wb = false;
+                }
+            }
+            if (wa) c.state[sa] = (uint8_t)ta;
+            if (wb) c.state[sb] = (uint8_t)tb;
+
+            double w = 0.0;
+            uint32_t gvnew = 0;
+            if (is_id) {
+                // join_idx (util.jl:15-23) -> diagonal vertex -> weight (sse.jl:156-162)
+                const uint32_t cidx = bi.z + (s_a - 1u) + (bi.x >> 24) * (s_b - 1u);
+                const uint32_t dv = st.diagv[cidx];
+                if (dv) { gvnew = dv - 1u; w = st.weights[gvnew]; }
+            } else if (is_dg) {
+                w = st.weights[gv];
+            }
+            // The accept tests depend on the running operator count n.  Solve the in-order recurrence by
+            // fixed-point iteration over the chunk: lane l only depends on lanes < l, so after i rounds the
+            // first i lanes are final; it stops when a round reproduces the masks (typically 2-3 rounds).
+            uint32_t ins = 0, rem = 0;
+            while (true) {
+                const int nl = n + __popc(ins & lt) - __popc(rem & lt);
+                bool acc = false;
+                if (is_id) {
+                    const double p_make_bond = p_make_bond_raw / (double)(M - nl);  // sse.jl:164
+                    acc = r < p_make_bond * w;                                       // sse.jl:166
+                } else if (is_dg) {
+                    const double p_remove_bond = (double)(M - nl + 1) * p_remove_bond_raw;  // sse.jl:176-177
+                    acc = r * w < p_remove_bond;                                             // sse.jl:178
+                }
+                const uint32_t ins2 = __ballot_sync(FULL, is_id && acc), rem2 = __ballot_sync(FULL, is_dg && acc);
+                if (ins2 == ins && rem2 == rem) break;
+                ins = ins2;
+                rem = rem2;
+            }
+            n += __popc(ins) - __popc(rem);
+            if (is_id && ((ins >> lane) & 1u)) newop = op_pack(bond, gvnew, 1u);
+            if (is_dg && ((rem >> lane) & 1u)) newop = 0u;
+        }
+
+        if (build) {
+            const bool nn = newop != 0u;
+            const uint32_t nm = __ballot_sync(FULL, nn);
+            const uint32_t k = kbase + __popc(nm & lt);
+            if ((long long)kbase + __popc(nm) > dw.n_cap) { c.flags |= SSE_FLAG_N_OVERFLOW; return; }
+            // nearest earlier / later operator of this chunk on each of my two sites
+            uint32_t pa = NONE24, pb = NONE24, sua = NONE24, sub = NONE24;
+            for (uint32_t m = nm; m;) {
+                const int L = __ffs(m) - 1;
+                m &= m - 1;
+                const uint32_t qa = __shfl_sync(FULL, sa, L), qb = __shfl_sync(FULL, sb, L);
+                const uint32_t qk = __shfl_sync(FULL, k, L) << 2;
+                if (nn && (int)lane > L) {
+                    if (sa == qa) pa = qk | 2u;
+                    if (sa == qb) pa = qk | 3u;
+                    if (sb == qa) pb = qk | 2u;
+                    if (sb == qb) pb = qk | 3u;
+                } else if (nn && (int)lane < L) {
+                    if (sua == NONE24) { if (sa == qa) sua = qk; else if (sa == qb) sua = qk | 1u; }
+                    if (sub == NONE24) { if (sb == qa) sub = qk; else if (sb == qb) sub = qk | 1u; }
+                }
+            }
+            uint32_t ma = NONE32, mb = NONE32;
+            if (nn) {
+                if (pa == NONE24) ma = c.vlast[sa];
+                if (pb == NONE24) mb = c.vlast[sb];
+            }
+            __syncwarp();
+            if (nn) {
+                const uint32_t me = k << 2;
+                uint32_t bla = pa, blb = pb;
+                if (pa == NONE24) {
+                    if (ma != NONE32) { bla = ma; rec_patch(c.rec, ma, me); }  // vertices[s1,p1] = (s,p) (vertex_list.jl:36-38)
+                    else c.vfirst[sa] = me;                                     // vertex_list.jl:40
+                }
+                if (pb == NONE24) {
+                    if (mb != NONE32) { blb = mb; rec_patch(c.rec, mb, me | 1u); }
+                    else c.vfirst[sb] = me | 1u;
+                }
+                if (sua == NONE24) c.vlast[sa] = me | 2u;  // vertex_list.jl:42
+                if (sub == NONE24) c.vlast[sb] = me | 3u;
+                c.rec[k] = rec_pack(newop, bla, blb, sua, sub);
+                c.ops[p] = k + 1u;
+            } else if (nonid) {
+                c.ops[p] = 0u;  // removed diagonal operator (sse.jl:179)
+            }
+            kbase += __popc(nm);
+        } else if (active && newop != op) {
+            c.ops[p] = newop;
+        }
+        __syncwarp();
+    }
+    if (build) {
+        // periodic closure (vertex_list.jl:46-51)
+        for (int s = lane; s < N; s += 32) {
+            const uint32_t f = c.vfirst[s];
+            if (f != NONE32) {
+                const uint32_t l = c.vlast[s];
+                rec_patch(c.rec, f, l);
+                rec_patch(c.rec, l, f);
+            }
+        }
+        __syncwarp();
+    }
+    c.n = n;
+    c.draws = draws;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// worm_traverse! inner loop (src/sse.jl:262-303) with scatter (src/vertex_data.jl:106-125).
+// All 32 lanes execute the chain uniformly; the lanes pre-compute the next 32 uniform draws in parallel.
+// ------------------------------------------------------------------------------------------------------
+template <bool INJ>
+__device__ unsigned long long worm_traverse(const SmTab &st, const DevModel &dm, Ctx &c, const uint32_t k0,
+                                            const uint32_t l0, const uint32_t w0) {
+    const int maxw = dm.max_worm;
+    uint32_t k = k0, leg = l0, wf = w0;
+    unsigned long long len = 1;
+    unsigned long long base = c.draws;
+    double rbuf = sse_u01(draw<INJ>(c, base + c.lane));
+    uint32_t ri = 0;
+    while (true) {
+        if (ri == 32) {
+            base += 32;
+            rbuf = sse_u01(draw<INJ>(c, base + c.lane));
+            ri = 0;
+        }
+        const double r = shfl_f64(rbuf, ri);  // rand(rng) (sse.jl:282)
+        ++ri;
+        const uint4 R = __ldcg(c.rec + k);
+        const uint32_t gv = op_gv(R.x);
+        const uint32_t t = st.trans[(gv * maxw + (wf - 1u)) * 4u + leg];  // transitions[leg_in, worm_in, vi]
+        const uint32_t off = t >> 10, cnt = t & 1023u;
+        uint32_t o = off;
+        uint4 e = st.outc[o];
+        bool hit = r < __hiloint2double((int)e.y, (int)e.x);
+        for (uint32_t j = 1; !hit && j < cnt; ++j) {  // first out with random < cumprob (vertex_data.jl:117-123)
+            o = off + j;
+            e = st.outc[o];
+            hit = r < __hiloint2double((int)e.y, (int)e.x);
+        }
+        if (!hit) c.flags |= SSE_FLAG_SCATTER_FALLTHROUGH;  // vertex_data.jl:124; clamped to the last outcome
+        const uint32_t pk = e.z;
+        const uint32_t leg_out = (pk >> 13) & 3u, w_out = (pk >> 15) & 0xffu, dim_out = (pk >> 23) & 0xffu;
+        const uint32_t newop = (R.x & ~(VMASK | 2u)) | ((pk & 0x1fffu) << 1);  // OperCode(bond, new_vertex) (sse.jl:285)
+        reinterpret_cast<uint32_t *>(c.rec + k)[0] = newop;
+        if (k == k0 && leg_out == l0 && w_out == dim_out - w0) break;  // sse.jl:288-290
+        ++len;
+        wf = w_out;
+        const uint32_t lk = rec_link(R, leg_out);  // (leg_in, p) = vertices[leg_out, p] (sse.jl:295)
+        k = lk >> 2;
+        leg = lk & 3u;
+        if (k == k0 && leg == l0 && wf == w0) break;  // sse.jl:297-299
+    }
+    c.draws = base + ri;
+    if (INJ && (long long)c.draws > c.inj_len) c.flags |= SSE_FLAG_STREAM_EXHAUSTED;
+    return len;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// worm_update (src/sse.jl:193-231) incl. worm_traverse! outer (src/sse.jl:233-260).  Needs indexed mode.
+// ------------------------------------------------------------------------------------------------------
+template <bool INJ>
+__device__ void phase_worm_update(const SmTab &st, const DevModel &dm, const DevWalkers &dw, Ctx &c, bool thermalized,
+                                  int widx) {
+    const uint32_t lane = c.lane, lt = lanemask_lt();
+    const int nworms = (int)ceil(c.num_worms);
+    double total = 1.0;  // sse.jl:194
+    for (int wi = 0; wi < nworms; ++wi) {
+        if (c.n == 0) continue;  // worm_traverse! returns 0 without drawing (sse.jl:234-236)
+        uint32_t k0 = 0, l0 = 0;
+        bool found = false;
+        while (!found) {
+            // rejection loop (sse.jl:241-247): 32 tries evaluated at once, the first success in order wins
+            if (INJ && (long long)c.draws >= c.inj_len) { c.flags |= SSE_FLAG_STREAM_EXHAUSTED; return; }
+            const uint32_t p0 = (uint32_t)sse_uint_below(draw<INJ>(c, c.draws + 2u * lane), (uint64_t)c.M);
+            const uint32_t ll = (uint32_t)sse_uint_below(draw<INJ>(c, c.draws + 2u * lane + 1u), 4u);
+            const uint32_t v = __ldcg(c.ops + p0);
+            const uint32_t ok = __ballot_sync(FULL, v != 0u);
+            if (ok) {
+                const int t = __ffs(ok) - 1;
+                k0 = __shfl_sync(FULL, v, t) - 1u;
+                l0 = __shfl_sync(FULL, ll, t);
+                c.draws += 2u * (unsigned)(t + 1);
+                found = true;
+            } else {
+                c.draws += 64u;
+            }
+        }
+        const uint4 R0 = __ldcg(c.rec + k0);
+        const uint4 bi = __ldg(dm.bond_info + op_bond(R0.x));
+        const uint32_t dim0 = (l0 & 1u) ? (bi.y >> 24) : (bi.x >> 24);  // site_of_leg (sse.jl:250)
+        const uint32_t w0 = 1u + (uint32_t)sse_uint_below(draw<INJ>(c, c.draws), dim0 - 1u);  // sse.jl:251
+        c.draws += 1;
+        const unsigned long long len = worm_traverse<INJ>(st, dm, c, k0, l0, w0);
+        total += (double)len;
+        c.visits += len;
+        if (c.flags & SSE_FLAG_STREAM_EXHAUSTED) return;
+    }
+    if (thermalized && c.n != 0) {  // sse.jl:200-202
+        c.last_wlf = total / (double)c.n;
+        if (lane == 0) {
+            dw.acc[(size_t)widx * dw.n_obs + SSE_OBS_WORM_LENGTH_FRACTION] += c.last_wlf;
+            dw.acc_cnt[2 * widx + 1] += 1;
+        }
+    }
+    const double avg_worm_length = total / ceil(c.num_worms);  // sse.jl:204
+    if (!thermalized) {                                        // sse.jl:205-217
+        c.avg_wl += dw.atten * (avg_worm_length - c.avg_wl);
+        const double target_worms = dw.twlf * (double)c.n / c.avg_wl;
+        c.num_worms += dw.atten * (target_worms - c.num_worms + 100.0 * sse_tanh(target_worms - c.num_worms));
+        if (dw.atten != 0) {
+            const double lo = 1.0, hi = 1.0 + (double)c.n / 2.0;
+            c.num_worms = c.num_worms < lo ? lo : (c.num_worms > hi ? hi : c.num_worms);
+        }
+    }
+    // rebuild the state from the first leg on each site; untouched sites are redrawn IN SITE ORDER (sse.jl:219-228)
+    const int N = dm.n_sites;
+    for (int b = 0; b < N; b += 32) {
+        const int s = b + (int)lane;
+        const bool act = s < N;
+        const uint32_t f = act ? c.vfirst[s] : 0u;
+        const bool empty = act && f == NONE32;
+        const uint32_t em = __ballot_sync(FULL, empty);
+        if (empty) {
+            const uint32_t d = dm.site_dim[s];
+            c.state[s] = (uint8_t)(1u + (uint32_t)sse_uint_below(draw<INJ>(c, c.draws + __popc(em & lt)), d));
+        } else if (act) {
+            const uint32_t op = __ldcg(reinterpret_cast<const uint32_t *>(c.rec + (f >> 2)));
+            c.state[s] = (uint8_t)((st.vinfo[op_gv(op)] >> (8u * (f & 3u))) & 0xffu);
+        }
+        c.draws += __popc(em);
+    }
+    if (INJ && (long long)c.draws > c.inj_len) c.flags |= SSE_FLAG_STREAM_EXHAUSTED;
+    __syncwarp();
+}
+
+// ------------------------------------------------------------------------------------------------------
+// K4C: commit the worm phase's vertices into the string (indexed -> committed) and, if asked, Carlo.measure!
+// (src/sse.jl:70-87): measure_sign (:305-314), the scalar observables, measure_opstring! (:321-376) with the
+// table-driven MagnetizationEstimator init/measure/result (magnetization_estimator.jl:96-230).
+// out[n_obs] (global) receives the observables.
+// ------------------------------------------------------------------------------------------------------
+__device__ void phase_commit_measure(const SmTab &st, const DevModel &dm, const DevWalkers &dw, Ctx &c, bool indexed,
+                                     bool do_measure, double *out) {
+    const uint32_t lane = c.lane;
+    const int M = c.M;
+    const int nchunks = (M + 31) >> 5;
+    uint32_t neg = 0;
+    if (indexed || do_measure) {
+        for (int ch = 0; ch < nchunks; ++ch) {
+            const int p = ch * 32 + (int)lane;
+            uint32_t op = p < M ? c.ops[p] : 0u;
+            if (indexed && op != 0u) {
+                op = __ldcg(reinterpret_cast<const uint32_t *>(c.rec + (op - 1u)));
+                c.ops[p] = op;
+            }
+            if (do_measure) neg += __popc(__ballot_sync(FULL, op != 0u && st.vneg[op_gv(op)]));
+        }
+        __syncwarp();
+    }
+    if (!do_measure) return;
+    const double sign = (neg & 1u) ? -1.0 : 1.0;  // sse.jl:313
+    const double nops = (double)c.n;
+    if (lane == 0) {
+        out[SSE_OBS_SIGN] = sign;
+        out[SSE_OBS_OPERATOR_COUNT] = nops;
+        out[SSE_OBS_SIGN_OPERATOR_COUNT] = sign * nops;
+        out[SSE_OBS_SIGN_OPERATOR_COUNT2] = sign * (nops * nops);
+        out[SSE_OBS_SIGN_ENERGY] = -sign * (nops * c.T + dm.energy_offset) / (double)dm.norm_sites;
+        out[SSE_OBS_WORM_LENGTH_FRACTION] = c.last_wlf;
+    }
+    const int N = dm.n_sites, md = dm.est_max_dim;
+    for (int e = 0; e < dm.n_est; ++e) {
+        const double *ev = dm.est_values + (size_t)e * N * md;
+        // init (magnetization_estimator.jl:96-123)
+        double part = 0.0;
+        for (int s = lane; s < N; s += 32) part += __ldg(ev + (size_t)s * md + (c.state[s] - 1));
+        double tmpmag = warp_sum_f64(part);
+        double mag = 0, absmag = 0, mag2 = 0, mag4 = 0;  // per-lane partial sums
+        if (lane == 0) { mag = tmpmag; absmag = fabs(tmpmag); mag2 = tmpmag * tmpmag; mag4 = mag2 * mag2; }
+        for (int ch = 0; ch < nchunks; ++ch) {
+            const int p = ch * 32 + (int)lane;
+            const uint32_t op = p < M ? c.ops[p] : 0u;
+            const bool nonid = op != 0u;
+            double delta = 0.0;
+            if (nonid && !(op & 2u)) {  // off-diagonal: tmpmag += sum_l sign*(m(top_l) - m(bottom_l)) (:134-150)
+                const uint4 bi = __ldg(dm.bond_info + op_bond(op));
+                const uint32_t vi = st.vinfo[op_gv(op)];
+                const double *ea = ev + (size_t)(bi.x & NONE24) * md, *eb = ev + (size_t)(bi.y & NONE24) * md;
+                delta = (__ldg(ea + ((vi >> 16) & 0xffu) - 1) - __ldg(ea + (vi & 0xffu) - 1)) +
+                        (__ldg(eb + (vi >> 24) - 1) - __ldg(eb + ((vi >> 8) & 0xffu) - 1));
+            }
+            double scan = delta;  // inclusive prefix sum over the chunk, in slot order
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const double up = shfl_up_f64(scan, d);
+                if ((int)lane >= d) scan += up;
+            }
+            if (nonid) {  // every non-identity operator is one sample (:152-158)
+                const double v = tmpmag + scan, v2 = v * v;
+                mag += v;
+                absmag += fabs(v);
+                mag2 += v2;
+                mag4 += v2 * v2;
+            }
+            tmpmag += shfl_f64(scan, 31);
+        }
+        mag = warp_sum_f64(mag);
+        absmag = warp_sum_f64(absmag);
+        mag2 = warp_sum_f64(mag2);
+        mag4 = warp_sum_f64(mag4);
+        if (lane == 0) {  // result (:205-230)
+            const double ns = 1.0 + nops;
+            const double norm = 1.0 / (double)dm.norm_sites;
+            mag *= norm;
+            absmag *= norm;
+            mag2 *= norm * norm;
+            mag4 *= (norm * norm) * (norm * norm);
+            double *o = out + SSE_OBS_FIXED + SSE_OBS_PER_ESTIMATOR * e;
+            o[0] = sign * mag / ns;
+            o[1] = sign * absmag / ns;
+            o[2] = sign * mag2 / ns;
+            o[3] = sign * mag4 / ns;
+            o[4] = sign * (1.0 / c.T / (ns + 1.0) / ns * (mag * mag + mag2) * (double)dm.norm_sites);
+        }
+    }
+    __syncwarp();
+}
+
+__device__ __forceinline__ SmTab stage_tables(const DevModel &dm, uint8_t *smem) {
+    const int n16 = dm.tl.bytes >> 4;
+    const uint4 *src = reinterpret_cast<const uint4 *>(dm.tab_blob);
+    uint4 *dst = reinterpret_cast<uint4 *>(smem);
+    for (int i = threadIdx.x; i < n16; i += blockDim.x) dst[i] = __ldg(src + i);
+    __syncthreads();
+    SmTab st;
+    st.outc = reinterpret_cast<const uint4 *>(smem + dm.tl.off_outc);
+    st.weights = reinterpret_cast<const double *>(smem + dm.tl.off_weights);
+    st.trans = reinterpret_cast<const uint32_t *>(smem + dm.tl.off_trans);
+    st.vinfo = reinterpret_cast<const uint32_t *>(smem + dm.tl.off_vinfo);
+    st.diagv = reinterpret_cast<const uint16_t *>(smem + dm.tl.off_diagv);
+    st.vneg = reinterpret_cast<const uint8_t *>(smem + dm.tl.off_vneg);
+    return st;
+}
+
+// The one kernel: every mode shares the phase code above.  One warp = one walker.
+template <bool INJ>
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 7) k_walkers(const DevModel dm, const DevWalkers dw, const LaunchArgs a) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const SmTab st = stage_tables(dm, smem);
+    const int w = blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5);
+    if (w >= dw.W) return;
+    Ctx c;
+    c.lane = threadIdx.x & 31;
+    c.ops = dw.ops + (size_t)w * dw.M_cap;
+    c.rec = dw.rec + (size_t)w * dw.n_cap;
+    c.state = dw.state + (size_t)w * dm.n_sites;
+    c.vfirst = dw.vfirst + (size_t)w * dm.n_sites;
+    c.vlast = dw.vlast + (size_t)w * dm.n_sites;
+    c.inj = INJ ? dw.inj + (size_t)w * dw.inj_len : nullptr;
+    c.inj_len = dw.inj_len;
+    c.seed = dw.seed;
+    c.wid = dw.wid_off + (unsigned long long)w;
+    c.draws = dw.draws[w];
+    c.T = dw.T[w];
+    c.num_worms = dw.num_worms[w];
+    c.avg_wl = dw.avg_wl[w];
+    c.last_wlf = dw.last_wlf[w];
+    c.M = dw.M[w];
+    c.n = dw.n[w];
+    c.flags = dw.flags[w];
+    c.visits = 0;
+    const uint32_t fatal = SSE_FLAG_M_OVERFLOW | SSE_FLAG_N_OVERFLOW | SSE_FLAG_STREAM_EXHAUSTED;
+    if (c.flags & fatal) return;
+    double *out = dw.obs_out + (size_t)w * dw.n_obs;
+    unsigned long long sweeps = 0, sum_n = 0, sum_M = 0;
+
+    switch (a.mode) {
+        case MODE_SWEEP:
+            for (int s = 0; s < a.n_sweeps && !(c.flags & fatal); ++s) {  // Carlo.sweep! (sse.jl:62-68)
+                phase_diag_build<INJ>(st, dm, dw, c, true, true);
+                if (c.flags & fatal) break;
+                phase_worm_update<INJ>(st, dm, dw, c, a.thermalized != 0, w);
+                if (c.flags & fatal) break;
+                phase_commit_measure(st, dm, dw, c, true, a.measure != 0, out);
+                ++sweeps;
+                sum_n += (unsigned long long)c.n;
+                sum_M += (unsigned long long)c.M;
+                if (a.measure) {
+                    __syncwarp();
+                    for (int i = c.lane; i < dw.n_obs; i += 32)
+                        if (i != SSE_OBS_WORM_LENGTH_FRACTION) dw.acc[(size_t)w * dw.n_obs + i] += out[i];
+                    if (c.lane == 0) dw.acc_cnt[2 * w] += 1;
+                    __syncwarp();
+                }
+            }
+            break;
+        case MODE_INIT: {  // Carlo.init! (sse.jl:47-60): M and the zeroed string are set by the host
+            for (int s = c.lane; s < dm.n_sites; s += 32)
+                c.state[s] = (uint8_t)(1u + (uint32_t)sse_uint_below(draw<INJ>(c, c.draws + s), dm.site_dim[s]));
+            c.draws += dm.n_sites;
+            __syncwarp();
+            for (int i = 0; i < a.warmup && !(c.flags & fatal); ++i) phase_diag_build<INJ>(st, dm, dw, c, true, false);
+            break;
+        }
+        case MODE_DIAG:
+            phase_diag_build<INJ>(st, dm, dw, c, true, false);
+            break;
+        case MODE_MAKE_VL:
+            phase_diag_build<INJ>(st, dm, dw, c, false, true);
+            break;
+        case MODE_WORM_UPDATE:
+            phase_worm_update<INJ>(st, dm, dw, c, a.thermalized != 0, w);
+            break;
+        case MODE_WORM_TRAVERSE: {
+            const uint32_t v = c.ops[a.p0];
+            long long len = -1;
+            if (v != 0u) len = (long long)worm_traverse<INJ>(st, dm, c, v - 1u, (uint32_t)a.l0, (uint32_t)a.w0);
+            if (c.lane == 0) dw.dbg_len[w] = len;
+            break;
+        }
+        case MODE_COMMIT:
+            phase_commit_measure(st, dm, dw, c, true, false, out);
+            break;
+        case MODE_MEASURE:
+            phase_commit_measure(st, dm, dw, c, a.indexed != 0, true, out);
+            break;
+    }
+    if (INJ && (long long)c.draws > c.inj_len) c.flags |= SSE_FLAG_STREAM_EXHAUSTED;
+    if (c.lane == 0) {
+        dw.draws[w] = c.draws;
+        dw.num_worms[w] = c.num_worms;
+        dw.avg_wl[w] = c.avg_wl;
+        dw.last_wlf[w] = c.last_wlf;
+        dw.M[w] = c.M;
+        dw.n[w] = c.n;
+        dw.flags[w] = c.flags;
+        if (c.visits) atomicAdd(dw.counters + 0, c.visits);
+        if (sweeps) {
+            atomicAdd(dw.counters + 1, sweeps);
+            atomicAdd(dw.counters + 2, sum_n);
+            atomicAdd(dw.counters + 3, sum_M);
+        }
+    }
+}
+
+}  // namespace sse

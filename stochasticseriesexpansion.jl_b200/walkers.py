@@ -1,0 +1,209 @@
+"""Object wrappers over the C ABI handles: `DeviceModel` (sse_model) and `Walkers` (sse_walkers).
+
+Thin: every method is one C call (see capi.py / include/sse_b200.h).  The Carlo-facing mirror of the
+reference's `MC` lives in mc.py on top of this.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+from .capi import WalkerState, WalkersOpts, check, f64p, i64p, u32p, u64p, u8p
+
+OBS_FIXED = ["Sign", "OperatorCount", "SignOperatorCount", "SignOperatorCount2", "SignEnergy", "WormLengthFraction"]
+OBS_PER_EST = ["Mag", "AbsMag", "Mag2", "Mag4", "MagChi"]
+
+
+class DeviceModel:
+    """sse_model: the flattened SSEData + estimator tables resident on the GPU."""
+
+    def __init__(self, model=None, desc=None, keep=None, sse_data=None):
+        if desc is None:
+            desc, keep, sse_data = capi.model_desc_from_model(model)
+        self.model, self.desc, self._keep, self.sse_data = model, desc, keep, sse_data
+        self.n_sites = int(desc.n_sites)
+        self.n_bonds = int(desc.n_bonds)
+        self.n_estimators = int(desc.n_estimators)
+        self.handle = C.c_void_p()
+        self.L = capi.lib()
+        check(self.L.sse_model_create(C.byref(desc), C.byref(self.handle)))
+
+    def observable_names(self):
+        names = list(OBS_FIXED)
+        ests = self.model.get_opstring_estimators() if self.model is not None else []
+        for e in range(self.n_estimators):
+            prefix = ests[e].prefix if e < len(ests) else f"Est{e}"
+            names += [f"Sign{prefix}{o}" for o in OBS_PER_EST]
+        return names
+
+    def close(self):
+        if getattr(self, "handle", None) is not None and self.handle:
+            self.L.sse_model_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Walkers:
+    """sse_walkers: a batch of independent walkers (each one reference `MC`, src/sse.jl:6-24)."""
+
+    def __init__(self, dmodel: DeviceModel, T, m_capacity: int, n_capacity: int | None = None, seed: int = 0,
+                 walker_id_offset: int = 0, device: int = -1, target_worm_length_fraction: float = 2.0,
+                 num_worms_attenuation_factor: float = 0.01, init_num_worms: float = 5.0):
+        self.dmodel = dmodel
+        self.L = capi.lib()
+        self.T = np.ascontiguousarray(np.atleast_1d(T), dtype=np.float64)
+        self.n_walkers = len(self.T)
+        o = WalkersOpts()
+        o.n_walkers = self.n_walkers
+        o.T = self.T.ctypes.data_as(f64p)
+        o.m_capacity = int(m_capacity)
+        o.n_capacity = int(n_capacity if n_capacity is not None else min(m_capacity, 1 << 22))
+        o.device = device
+        o.seed = seed
+        o.walker_id_offset = walker_id_offset
+        o.target_worm_length_fraction = target_worm_length_fraction
+        o.num_worms_attenuation_factor = num_worms_attenuation_factor
+        o.init_num_worms = init_num_worms
+        self.m_capacity = o.m_capacity
+        self.handle = C.c_void_p()
+        check(self.L.sse_walkers_create(dmodel.handle, C.byref(o), C.byref(self.handle)))
+        self.n_obs = int(self.L.sse_n_observables(self.handle))
+
+    def close(self):
+        if getattr(self, "handle", None) is not None and self.handle:
+            self.L.sse_walkers_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # --- Carlo.AbstractMC surface ------------------------------------------------------------------
+    def set_stream(self, cuda_stream: int):
+        check(self.L.sse_set_stream(self.handle, C.c_void_p(cuda_stream)))
+
+    def device_bytes(self) -> int:
+        return int(self.L.sse_device_bytes(self.handle))
+
+    def init(self, init_opstring_cutoff: int = -1, diagonal_warmup_sweeps: int = 5):
+        check(self.L.sse_init(self.handle, init_opstring_cutoff, diagonal_warmup_sweeps))
+
+    def sweep(self, n_sweeps: int = 1, thermalized: bool = False, measure: bool = False, sync: bool = True):
+        check(self.L.sse_sweep(self.handle, n_sweeps, int(thermalized), int(measure)))
+        if sync:
+            self.sync()
+
+    def sync(self):
+        check(self.L.sse_sync(self.handle))
+
+    def measure(self) -> np.ndarray:
+        out = np.zeros((self.n_walkers, self.n_obs))
+        check(self.L.sse_measure(self.handle, out.ctypes.data_as(f64p)))
+        return out
+
+    def fetch_accumulators(self, reset: bool = True):
+        sums = np.zeros((self.n_walkers, self.n_obs))
+        counts = np.zeros((self.n_walkers, 2), dtype=np.int64)
+        check(self.L.sse_fetch_accumulators(self.handle, sums.ctypes.data_as(f64p), counts.ctypes.data_as(i64p), int(reset)))
+        return sums, counts
+
+    def accumulators_device_ptr(self):
+        s, c = C.c_void_p(), C.c_void_p()
+        check(self.L.sse_accumulators_device_ptr(self.handle, C.byref(s), C.byref(c)))
+        return s.value, c.value
+
+    def fetch_counters(self, reset: bool = False) -> dict:
+        out = np.zeros(4, dtype=np.uint64)
+        check(self.L.sse_fetch_counters(self.handle, out.ctypes.data_as(u64p), int(reset)))
+        return dict(visits=int(out[0]), sweeps=int(out[1]), sum_n=int(out[2]), sum_M=int(out[3]))
+
+    def get_state(self, walker: int) -> dict:
+        ops = np.zeros(self.m_capacity + 32, dtype=np.uint64)
+        state = np.zeros(self.dmodel.n_sites, dtype=np.uint8)
+        st = WalkerState()
+        st.operators = ops.ctypes.data_as(u64p)
+        st.operators_len = len(ops)
+        st.state = state.ctypes.data_as(u8p)
+        check(self.L.sse_get_state(self.handle, walker, C.byref(st)))
+        return dict(num_operators=int(st.num_operators), avg_worm_length=float(st.avg_worm_length),
+                    num_worms=float(st.num_worms), operators=ops[: st.operators_len].copy(), state=state,
+                    rng_draws=int(st.rng_draws), T=float(st.T))
+
+    def set_state(self, walker: int, s: dict):
+        ops = np.ascontiguousarray(s["operators"], dtype=np.uint64)
+        state = np.ascontiguousarray(s["state"], dtype=np.uint8)
+        st = WalkerState()
+        st.num_operators = int(s["num_operators"])
+        st.avg_worm_length = float(s.get("avg_worm_length", 1.0))
+        st.num_worms = float(s.get("num_worms", 5.0))
+        st.operators = ops.ctypes.data_as(u64p)
+        st.operators_len = len(ops)
+        st.state = state.ctypes.data_as(u8p)
+        st.rng_draws = int(s.get("rng_draws", 0))
+        st.T = float(s["T"])
+        check(self.L.sse_set_state(self.handle, walker, C.byref(st)))
+
+    def get_flags(self) -> np.ndarray:
+        f = np.zeros(self.n_walkers, dtype=np.uint32)
+        check(self.L.sse_get_flags(self.handle, f.ctypes.data_as(u32p)))
+        return f
+
+    def num_operators(self) -> np.ndarray:
+        n = np.zeros(self.n_walkers, dtype=np.int64)
+        check(self.L.sse_get_num_operators(self.handle, n.ctypes.data_as(i64p)))
+        return n
+
+    def pt_log_weight_ratio(self, new_T) -> np.ndarray:
+        nt = np.ascontiguousarray(new_T, dtype=np.float64)
+        out = np.zeros(self.n_walkers)
+        check(self.L.sse_pt_log_weight_ratio(self.handle, nt.ctypes.data_as(f64p), out.ctypes.data_as(f64p)))
+        return out
+
+    def set_temperature(self, T):
+        t = np.ascontiguousarray(T, dtype=np.float64)
+        assert len(t) == self.n_walkers
+        check(self.L.sse_set_temperature(self.handle, t.ctypes.data_as(f64p)))
+        self.T = t
+
+    # --- parity hooks ------------------------------------------------------------------------------
+    def set_injected_stream(self, stream):
+        if stream is None:
+            check(self.L.sse_set_injected_stream(self.handle, None, 0))
+            return
+        s = np.ascontiguousarray(stream, dtype=np.uint64)
+        assert s.ndim == 2 and s.shape[0] == self.n_walkers
+        check(self.L.sse_set_injected_stream(self.handle, s.ctypes.data_as(u64p), s.shape[1]))
+
+    def dbg_diagonal_update(self):
+        check(self.L.sse_dbg_diagonal_update(self.handle))
+
+    def dbg_make_vertex_list(self):
+        check(self.L.sse_dbg_make_vertex_list(self.handle))
+
+    def dbg_worm_update(self, thermalized: bool = False):
+        check(self.L.sse_dbg_worm_update(self.handle, int(thermalized)))
+
+    def dbg_worm_traverse(self, l0: int, p0: int, wormfunc0: int) -> np.ndarray:
+        out = np.zeros(self.n_walkers, dtype=np.int64)
+        check(self.L.sse_dbg_worm_traverse(self.handle, l0, p0, wormfunc0, out.ctypes.data_as(i64p)))
+        return out
+
+    def dbg_get_vertex_list(self, walker: int, M: int):
+        v = np.zeros((M, 4, 2), dtype=np.int64)
+        vf = np.zeros((self.dmodel.n_sites, 2), dtype=np.int64)
+        vl = np.zeros((self.dmodel.n_sites, 2), dtype=np.int64)
+        check(self.L.sse_dbg_get_vertex_list(self.handle, walker, v.ctypes.data_as(i64p), M, vf.ctypes.data_as(i64p),
+                                             vl.ctypes.data_as(i64p)))
+        return v, vf, vl
+
+    def dbg_commit(self):
+        check(self.L.sse_dbg_commit(self.handle))
