@@ -8,8 +8,9 @@
  *     them in exactly the reference's order;
  *   - U()  = (x >> 11) * 2^-53              uniform double in [0,1)        (replaces rand(rng))
  *   - I(k) = 1 + mulhi64(x, k)              uniform integer in 1..k        (replaces rand(rng, 1:k))
- *   - production stream: x_k = low 64 bits of Philox4x32-10(counter = (k_lo, k_hi, walker_lo, walker_hi),
- *     key = (seed_lo, seed_hi)); debug/parity stream: an explicit uint64 array ("injected stream").
+ *   - production stream: Philox4x32-10 block j = philox(counter = (j_lo, j_hi, walker_lo, walker_hi),
+ *     key = (seed_lo, seed_hi)) yields draws x_{2j} = words (0,1) and x_{2j+1} = words (2,3);
+ *     debug/parity stream: an explicit uint64 array ("injected stream").
  *
  * Both the CUDA kernels and the CPU oracle include this file, so the two sides cannot drift.
  * Also here: a portable tanh built from IEEE +,-,*,/ only (no FMA contraction: compile with
@@ -44,9 +45,10 @@ SSE_HD uint64_t sse_mulhi64(uint64_t a, uint64_t b) {
 #endif
 }
 
-/* Philox4x32-10 (Salmon et al., SC'11), returns the low 64 bits (words 0 and 1) of the block. */
-SSE_HD uint64_t sse_philox_draw(uint64_t seed, uint64_t walker, uint64_t k) {
-    uint32_t c0 = (uint32_t)k, c1 = (uint32_t)(k >> 32), c2 = (uint32_t)walker, c3 = (uint32_t)(walker >> 32);
+/* Philox4x32-10 (Salmon et al., SC'11): block j of walker `walker` under key `seed`;
+ * counter = (j_lo, j_hi, walker_lo, walker_hi), key = (seed_lo, seed_hi). */
+SSE_HD void sse_philox_block(uint64_t seed, uint64_t walker, uint64_t j, uint32_t out[4]) {
+    uint32_t c0 = (uint32_t)j, c1 = (uint32_t)(j >> 32), c2 = (uint32_t)walker, c3 = (uint32_t)(walker >> 32);
     uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
 #if defined(__CUDA_ARCH__)
 #pragma unroll
@@ -59,7 +61,15 @@ SSE_HD uint64_t sse_philox_draw(uint64_t seed, uint64_t walker, uint64_t k) {
         c0 = n0; c1 = n1; c2 = n2; c3 = n3;
         k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
     }
-    return (uint64_t)c0 | ((uint64_t)c1 << 32);
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+/* Draw k of the production stream: one Philox block yields two draws,
+ * x_{2j} = words (0,1) and x_{2j+1} = words (2,3) of block j. */
+SSE_HD uint64_t sse_philox_draw(uint64_t seed, uint64_t walker, uint64_t k) {
+    uint32_t b[4];
+    sse_philox_block(seed, walker, k >> 1, b);
+    return (k & 1) ? ((uint64_t)b[2] | ((uint64_t)b[3] << 32)) : ((uint64_t)b[0] | ((uint64_t)b[1] << 32));
 }
 
 /* U(): uniform double in [0,1) from a raw draw. */

@@ -192,6 +192,8 @@ struct Rng {
     uint64_t stream_len = 0;
     bool exhausted = false;
     uint64_t s[4] = {1, 2, 3, 4};
+    uint64_t cached_j = ~0ull;
+    uint32_t cached[4] = {0, 0, 0, 0};
     static inline uint64_t rotl(uint64_t x, int k) { return (x << k) | (x >> (64 - k)); }
     void seed_xoshiro(uint64_t sd) {  // splitmix64 expansion
         for (int i = 0; i < 4; ++i) {
@@ -213,7 +215,11 @@ struct Rng {
             if (k >= stream_len) { exhausted = true; return 0; }
             return stream[k];
         }
-        return sse_philox_draw(seed, walker, k);
+        if ((k >> 1) != cached_j) {  // one Philox block = two draws (include/sse_rng.h)
+            cached_j = k >> 1;
+            sse_philox_block(seed, walker, cached_j, cached);
+        }
+        return (k & 1) ? (uint64_t(cached[2]) | (uint64_t(cached[3]) << 32)) : (uint64_t(cached[0]) | (uint64_t(cached[1]) << 32));
     }
     inline double U() { return sse_u01(next()); }                       // rand(rng)
     inline Int I(Int k) { return 1 + Int(sse_uint_below(next(), uint64_t(k))); }  // rand(rng, 1:k)

@@ -88,7 +88,11 @@ int32_t launch(sse_walkers *w, const LaunchArgs &a) {
     CU(cudaSetDevice(m->device));
     const int grid = (w->dw.W + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
     const int block = WARPS_PER_CTA * 32;
-    const size_t smem = (size_t)m->dm.tl.bytes;
+    const size_t smem = (size_t)m->dm.tl.bytes + (size_t)WARPS_PER_CTA * warp_scratch_bytes(m->dm.n_sites, w->dw.smem_state);
+    if (smem > 48 * 1024) {
+        CU(cudaFuncSetAttribute(k_walkers<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CU(cudaFuncSetAttribute(k_walkers<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
     if (w->dw.inj)
         k_walkers<true><<<grid, block, smem, w->stream>>>(m->dm, w->dw, a);
     else
@@ -172,18 +176,18 @@ int32_t sse_model_create(const sse_model_desc *d, sse_model **out) {
     TabLayout tl{};
     int off = 0;
     auto take = [&](int bytes) { int o = off; off += (bytes + 15) & ~15; return o; };
+    tl.off_t1 = take(16 * n_trans);
     tl.off_outc = take(16 * n_out);
     tl.off_weights = take(8 * nv);
-    tl.off_trans = take(4 * n_trans);
     tl.off_vinfo = take(4 * nv);
     tl.off_diagv = take(2 * n_diag);
     tl.off_vneg = take(nv);
     tl.bytes = off;
-    if (tl.bytes > 96 * 1024) { delete m; return fail("sse_model_create: vertex tables exceed the 96 KB shared-memory budget"); }
+    if (tl.bytes > 64 * 1024) { delete m; return fail("sse_model_create: vertex tables exceed the 64 KB shared-memory budget"); }
     std::vector<uint8_t> blob(tl.bytes, 0);
     auto *outc = reinterpret_cast<uint4 *>(blob.data() + tl.off_outc);
     auto *wts = reinterpret_cast<double *>(blob.data() + tl.off_weights);
-    auto *trans = reinterpret_cast<uint32_t *>(blob.data() + tl.off_trans);
+    auto *t1 = reinterpret_cast<uint4 *>(blob.data() + tl.off_t1);
     auto *vinfo = reinterpret_cast<uint32_t *>(blob.data() + tl.off_vinfo);
     auto *diagv = reinterpret_cast<uint16_t *>(blob.data() + tl.off_diagv);
     auto *vneg = blob.data() + tl.off_vneg;
@@ -202,9 +206,8 @@ int32_t sse_model_create(const sse_model_desc *d, sse_model **out) {
     std::vector<int> otype(n_out, -1);
     for (int i = 0; i < n_trans; ++i) {
         int o = d->trans_offset[i], c = d->trans_count[i];
-        if (o < 0) { trans[i] = NONE32; continue; }
+        if (o < 0) continue;
         if (c < 1 || c > 1023 || o + c > n_out || o >= (1 << 22)) { delete m; return fail("sse_model_create: bad transition entry"); }
-        trans[i] = ((uint32_t)o << 10) | (uint32_t)c;
         int v = i / (d->max_worm * 4);
         for (int j = 0; j < c; ++j) otype[o + j] = vtype[v];
     }
@@ -228,6 +231,12 @@ int32_t sse_model_create(const sse_model_desc *d, sse_model **out) {
         memcpy(&bits, &cp, 8);
         outc[o] = make_uint4((uint32_t)bits, (uint32_t)(bits >> 32), pk, 0u);
     }
+    // transition header fused with its first outcome; invalid transitions get cumprob +inf and step 0
+    for (int i = 0; i < n_trans; ++i) {
+        int o = d->trans_offset[i], c = d->trans_count[i];
+        if (o < 0) { t1[i] = make_uint4(0u, 0x7ff00000u, 0u, 0u); continue; }
+        t1[i] = make_uint4(outc[o].x, outc[o].y, outc[o].z, ((uint32_t)(o + 1) << 10) | (uint32_t)(c - 1));
+    }
     CU(upload(&m->d_bond_info, bi));
     CU(upload(&m->d_site_dim, m->site_dim));
     CU(upload(&m->d_blob, blob));
@@ -248,10 +257,6 @@ int32_t sse_model_create(const sse_model_desc *d, sse_model **out) {
     dm.est_values = m->d_est;
     dm.tab_blob = m->d_blob;
     dm.tl = tl;
-    if (tl.bytes > 48 * 1024) {
-        CU(cudaFuncSetAttribute(k_walkers<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tl.bytes));
-        CU(cudaFuncSetAttribute(k_walkers<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tl.bytes));
-    }
     *out = m;
     return 0;
 }
@@ -285,6 +290,9 @@ int32_t sse_walkers_create(const sse_model *m, const sse_walkers_opts *o, sse_wa
     s |= dev_alloc(w, &dw.ops, (size_t)W * dw.M_cap, true);
     s |= dev_alloc(w, &dw.rec, (size_t)W * dw.n_cap, false);
     s |= dev_alloc(w, &dw.state, (size_t)W * N, false);
+    // per-warp state[N] + mark[N] live in shared memory when 7 CTAs/SM still fit, else in global scratch
+    dw.smem_state = (m->dm.tl.bytes + WARPS_PER_CTA * warp_scratch_bytes(N, 1) <= 99 * 1024) ? 1 : 0;
+    if (!dw.smem_state) s |= dev_alloc(w, &dw.mark, (size_t)W * N, true);
     s |= dev_alloc(w, &dw.vfirst, (size_t)W * N, false);
     s |= dev_alloc(w, &dw.vlast, (size_t)W * N, false);
     s |= dev_alloc(w, &dw.T, W, true);

@@ -13,9 +13,11 @@
 //                          visit's only store goes back into the same sector.
 //   state[W][N] u8, vfirst/vlast [W][N] u32 (link of the first / last leg on each site's world line).
 //
-// The (<16 KB) vertex tables are staged in shared memory once per CTA.  Warp primitives do the scans:
-// ballot/popc prefix sums give each slot its random-stream offset (2/1/0 draws by pre-update slot type) and
-// its compact record index; shuffles resolve same-site ordering inside a 32-slot chunk.
+// Shared memory per CTA: the vertex tables (staged once) + per warp: the walker's state[N], a mark[N] byte
+// array used to detect same-site collisions inside a 32-slot chunk, and a 66-word random-draw scratch.
+// Warp primitives do the scans: ballot/popc prefix sums give each slot its random-stream offset (2/1/0
+// draws by pre-update slot type) and its compact record index; one Philox block per lane feeds a whole
+// chunk; shuffles resolve same-site ordering only in the rare chunks where two operators share a site.
 //
 // Every phase reproduces the reference's draw ORDER and its Float64 expressions
 // (no FMA contraction: compile with -fmad=false), so results are bit-identical to the CPU oracle under
@@ -36,6 +38,7 @@ constexpr int VBITS = 12;                 // global vertex id bits in the device
 constexpr uint32_t VMASK = ((1u << VBITS) - 1u) << 2;  // bits 2..13
 constexpr int BOND_SHIFT = 2 + VBITS;     // 14
 constexpr int WARPS_PER_CTA = 4;
+constexpr int RNG_WORDS = 66;             // 33 Philox blocks x 2 draws (see phase_diag_build)
 
 __host__ __device__ __forceinline__ uint32_t op_pack(uint32_t bond, uint32_t gv, uint32_t diag) {
     return 1u | (diag << 1) | (gv << 2) | (bond << BOND_SHIFT);
@@ -46,19 +49,20 @@ __host__ __device__ __forceinline__ uint32_t op_bond(uint32_t op) { return op >>
 // Shared-memory image of the vertex tables (built once on the host, copied per CTA).
 struct TabLayout {
     int bytes;
+    int off_t1;       // uint4  [nv*max_worm*4] first outcome fused with the transition header:
+                      //        {cumprob0 lo, cumprob0 hi, packed step0, (offset of outcome 1 << 10) | remaining count}
     int off_outc;     // uint4  [n_outcomes] {cumprob lo, cumprob hi, packed step, 0}
     int off_weights;  // double [nv]
-    int off_trans;    // u32    [nv*max_worm*4]  (offset << 10) | count, NONE32 = invalid
     int off_vinfo;    // u32    [nv]  leg states packed, 8 bits per leg
     int off_diagv;    // u16    [n_diag]  global vertex id + 1, 0 = invalid
     int off_vneg;     // u8     [nv]  1 if the vertex sign is negative
 };
-// outcome.z: bit0 = diagonal flag of the target, bits 1..12 = target gv, bits 13..14 = exit leg,
-//            bits 15..22 = exit worm, bits 23..30 = dim of the exit leg's site
+// packed step: bit0 = diagonal flag of the target, bits 1..12 = target gv, bits 13..14 = exit leg,
+//              bits 15..22 = exit worm, bits 23..30 = dim of the exit leg's site
 struct SmTab {
+    const uint4 *t1;
     const uint4 *outc;
     const double *weights;
-    const uint32_t *trans;
     const uint32_t *vinfo;
     const uint16_t *diagv;
     const uint8_t *vneg;
@@ -80,6 +84,7 @@ struct DevWalkers {
     uint32_t *ops;
     uint4 *rec;
     uint8_t *state;
+    uint8_t *mark;               // [W][N] scratch, only used when the per-warp arrays do not fit in shared memory
     uint32_t *vfirst, *vlast;
     double *T;
     int *M, *n;
@@ -96,6 +101,7 @@ struct DevWalkers {
     unsigned long long seed, wid_off;
     double twlf, atten;
     int n_obs;
+    int smem_state;              // 1: state/mark arrays live in shared memory
 };
 
 enum Mode : int {
@@ -113,7 +119,9 @@ struct LaunchArgs {
 struct Ctx {
     uint32_t *ops;
     uint4 *rec;
-    uint8_t *state;
+    uint8_t *state;              // generic pointer: shared memory or the global array
+    uint8_t *mark;
+    unsigned long long *rng;     // per-warp shared scratch, RNG_WORDS entries
     uint32_t *vfirst, *vlast;
     const unsigned long long *inj;
     long long inj_len;
@@ -134,6 +142,22 @@ template <bool INJ>
 __device__ __forceinline__ uint64_t draw(const Ctx &c, unsigned long long k) {
     if (INJ) return (long long)k < c.inj_len ? (uint64_t)__ldg(c.inj + k) : 0ull;
     return sse_philox_draw(c.seed, c.wid, k);
+}
+
+// Fill the warp's scratch with the draws [2*j0, 2*j0 + 64): lane L computes Philox block j0 + L (two draws).
+template <bool INJ>
+__device__ __forceinline__ void fill_draws(const Ctx &c, unsigned long long j0) {
+    if (!INJ) {
+        uint32_t b[4];
+        sse_philox_block(c.seed, c.wid, j0 + c.lane, b);
+        reinterpret_cast<uint4 *>(c.rng)[c.lane] = make_uint4(b[0], b[1], b[2], b[3]);
+    }
+}
+// Draw with absolute index k from the scratch filled by fill_draws(j0) (or from the injected stream).
+template <bool INJ>
+__device__ __forceinline__ uint64_t scratch_draw(const Ctx &c, unsigned long long j0, unsigned long long k) {
+    if (INJ) return (long long)k < c.inj_len ? (uint64_t)__ldg(c.inj + k) : 0ull;
+    return c.rng[k - 2ull * j0];
 }
 
 // link j (24 bits) of a record: bits [24j, 24j+24) of the 96-bit little-endian field (y, z, w)
@@ -199,8 +223,8 @@ __device__ void phase_diag_build(const SmTab &st, const DevModel &dm, const DevW
     }
     if (build) {
         for (int s = lane; s < N; s += 32) { c.vfirst[s] = NONE32; c.vlast[s] = NONE32; }
-        __syncwarp();
     }
+    __syncwarp();
     const int M = c.M;
     const uint32_t Nb = (uint32_t)dm.n_bonds;
     const double p_make_bond_raw = (double)dm.n_bonds / c.T;   // sse.jl:147
@@ -209,11 +233,13 @@ __device__ void phase_diag_build(const SmTab &st, const DevModel &dm, const DevW
     uint32_t kbase = 0;
     unsigned long long draws = c.draws;
     const int nchunks = (M + 31) >> 5;
+    uint32_t op_next = ((int)lane < M) ? c.ops[lane] : 0u;
 
     for (int ch = 0; ch < nchunks; ++ch) {
         const int p = ch * 32 + (int)lane;
         const bool active = p < M;
-        const uint32_t op = active ? c.ops[p] : 0u;
+        const uint32_t op = op_next;
+        op_next = (p + 32 < M) ? c.ops[p + 32] : 0u;  // prefetch the next chunk
         const bool nonid = op != 0u;
         const bool is_id = active && !nonid;
         const bool is_dg = nonid && (op & 2u);
@@ -222,50 +248,91 @@ __device__ void phase_diag_build(const SmTab &st, const DevModel &dm, const DevW
         const uint32_t gv = op_gv(op);
         uint32_t newop = op;
         double r = 0.0;
+        uint32_t idm = 0, dgm = 0;
 
         if (do_diag) {
             // stream offsets: 2 draws per identity slot, 1 per diagonal operator, in slot order (Appendix A)
-            const uint32_t idm = __ballot_sync(FULL, is_id), dgm = __ballot_sync(FULL, is_dg);
-            const unsigned long long my = draws + 2u * __popc(idm & lt) + __popc(dgm & lt);
-            if (is_id) {
-                bond = (uint32_t)sse_uint_below(draw<INJ>(c, my), Nb);  // rand(rng, 1:N_b) - 1 (sse.jl:152)
-                r = sse_u01(draw<INJ>(c, my + 1));                      // sse.jl:166
-            } else if (is_dg) {
-                r = sse_u01(draw<INJ>(c, my));                          // sse.jl:178
+            idm = __ballot_sync(FULL, is_id);
+            dgm = __ballot_sync(FULL, is_dg);
+            const uint32_t D = 2u * __popc(idm) + __popc(dgm);
+            if (D) {
+                const unsigned long long my = draws + 2u * __popc(idm & lt) + __popc(dgm & lt);
+                const unsigned long long j0 = draws >> 1;
+                fill_draws<INJ>(c, j0);
+                if (!INJ && (draws & 1ull) && D == 64u && lane == 0) {  // the one draw beyond 32 blocks
+                    uint32_t b[4];
+                    sse_philox_block(c.seed, c.wid, j0 + 32, b);
+                    reinterpret_cast<uint4 *>(c.rng)[32] = make_uint4(b[0], b[1], b[2], b[3]);
+                }
+                __syncwarp();
+                if (is_id) {
+                    bond = (uint32_t)sse_uint_below(scratch_draw<INJ>(c, j0, my), Nb);  // rand(rng, 1:N_b) - 1 (sse.jl:152)
+                    r = sse_u01(scratch_draw<INJ>(c, j0, my + 1));                      // sse.jl:166
+                } else if (is_dg) {
+                    r = sse_u01(scratch_draw<INJ>(c, j0, my));                          // sse.jl:178
+                }
+                draws += D;
             }
-            draws += 2u * __popc(idm) + __popc(dgm);
         }
         uint4 bi = make_uint4(0, 0, 0, 0);
         if (is_id || nonid) bi = __ldg(dm.bond_info + bond);
         const uint32_t sa = bi.x & NONE24, sb = bi.y & NONE24;
 
         if (do_diag) {
-            // state seen by each identity slot = state at chunk start overridden by earlier off-diagonal
-            // operators of this chunk (sse.jl:182-188)
+            // State seen by each identity slot = state at chunk start overridden by earlier off-diagonal
+            // operators of this chunk (sse.jl:182-188).  Off-diagonal lanes tag their sites in mark[]; only if
+            // an identity lane reads a tagged site, or two off-diagonal lanes share a site, the in-order
+            // shuffle loop runs.
             const uint32_t offm = __ballot_sync(FULL, is_off);
             uint32_t s_a = 1, s_b = 1, ta = 0, tb = 0;
-            if (is_id) { s_a = c.state[sa]; s_b = c.state[sb]; }
-            if (is_off) { const uint32_t vi = st.vinfo[gv]; ta = (vi >> 16) & 0xffu; tb = vi >> 24; }
-            bool wa = is_off, wb = is_off;
-            __syncwarp();
-            for (uint32_t m = offm; m;) {
-                const int L = __ffs(m) - 1;
-                m &= m - 1;
-                const uint32_t qa = __shfl_sync(FULL, sa, L), qb = __shfl_sync(FULL, sb, L);
-                const uint32_t qta = __shfl_sync(FULL, ta, L), qtb = __shfl_sync(FULL, tb, L);
-                if (is_id && (int)lane > L) {
-                    if (sa == qa) s_a = qta;
-                    if (sa == qb) s_a = qtb;
-                    if (sb == qa) s_b = qta;
-                    if (sb == qb) s_b = qtb;
+            if (offm) {
+                const uint8_t tag = (uint8_t)(0x80u | lane);
+                if (is_off) {
+                    const uint32_t vi = st.vinfo[gv];
+                    ta = (vi >> 16) & 0xffu;
+                    tb = vi >> 24;
+                    c.mark[sa] = tag;
+                    c.mark[sb] = tag;
                 }
-                if (is_off && (int)lane < L) {  // a later operator of the chunk overwrites this site
-                    if (sa == qa || sa == qb) wa = false;
-                    if (sb == qa || sb == qb) wb = false;
+                __syncwarp();
+                bool hit = false;
+                if (is_off) hit = (c.mark[sa] != tag) || (c.mark[sb] != tag);
+                if (is_id) {
+                    hit = ((c.mark[sa] | c.mark[sb]) & 0x80u) != 0;
+                    s_a = c.state[sa];
+                    s_b = c.state[sb];
                 }
+                const uint32_t anyhit = __ballot_sync(FULL, hit);
+                __syncwarp();
+                bool wa = is_off, wb = is_off;
+                if (anyhit) {
+                    for (uint32_t m = offm; m;) {
+                        const int L = __ffs(m) - 1;
+                        m &= m - 1;
+                        const uint32_t qa = __shfl_sync(FULL, sa, L), qb = __shfl_sync(FULL, sb, L);
+                        const uint32_t qta = __shfl_sync(FULL, ta, L), qtb = __shfl_sync(FULL, tb, L);
+                        if (is_id && (int)lane > L) {
+                            if (sa == qa) s_a = qta;
+                            if (sa == qb) s_a = qtb;
+                            if (sb == qa) s_b = qta;
+                            if (sb == qb) s_b = qtb;
+                        }
+                        if (is_off && (int)lane < L) {  // a later operator of the chunk overwrites this site
+                            if (sa == qa || sa == qb) wa = false;
+                            if (sb == qa || sb == qb) wb = false;
+                        }
+                    }
+                }
+                if (is_off) {
+                    if (wa) c.state[sa] = (uint8_t)ta;
+                    if (wb) c.state[sb] = (uint8_t)tb;
+                    c.mark[sa] = 0;
+                    c.mark[sb] = 0;
+                }
+            } else if (is_id) {
+                s_a = c.state[sa];
+                s_b = c.state[sb];
             }
-            if (wa) c.state[sa] = (uint8_t)ta;
-            if (wb) c.state[sb] = (uint8_t)tb;
 
             double w = 0.0;
             uint32_t gvnew = 0;
@@ -277,24 +344,46 @@ __device__ void phase_diag_build(const SmTab &st, const DevModel &dm, const DevW
             } else if (is_dg) {
                 w = st.weights[gv];
             }
-            // The accept tests depend on the running operator count n.  Solve the in-order recurrence by
-            // fixed-point iteration over the chunk: lane l only depends on lanes < l, so after i rounds the
-            // first i lanes are final; it stops when a round reproduces the masks (typically 2-3 rounds).
-            uint32_t ins = 0, rem = 0;
-            while (true) {
-                const int nl = n + __popc(ins & lt) - __popc(rem & lt);
-                bool acc = false;
-                if (is_id) {
-                    const double p_make_bond = p_make_bond_raw / (double)(M - nl);  // sse.jl:164
-                    acc = r < p_make_bond * w;                                       // sse.jl:166
-                } else if (is_dg) {
-                    const double p_remove_bond = (double)(M - nl + 1) * p_remove_bond_raw;  // sse.jl:176-177
-                    acc = r * w < p_remove_bond;                                             // sse.jl:178
+            // Accept tests (sse.jl:164-166,176-178) depend on the running operator count n.  Within the chunk
+            // n stays in [n - #diagonal, n + #identity]; both tests are monotone in n (IEEE division and
+            // multiplication are monotone), so evaluating them at the two ends decides every lane whose draw is
+            // not between the two thresholds.  Only if some lane is undecided (probability ~ 64/(M-n) per chunk)
+            // the in-order recurrence is solved exactly by fixed-point iteration.
+            const int n_lo = n - __popc(dgm), n_hi = n + __popc(idm);
+            bool acc = false, amb = false;
+            if (is_id) {
+                const double pm_lo = p_make_bond_raw / (double)(M - n_lo);
+                const double pm_hi = (M - n_hi > 0) ? p_make_bond_raw / (double)(M - n_hi) : __longlong_as_double(0x7ff0000000000000ll);
+                acc = r < pm_lo * w;
+                amb = !acc && (r < pm_hi * w);
+            } else if (is_dg) {
+                const double rw = r * w;
+                acc = rw < (double)(M - n_hi + 1) * p_remove_bond_raw;
+                amb = !acc && (rw < (double)(M - n_lo + 1) * p_remove_bond_raw);
+            }
+            uint32_t ins, rem;
+            if (__ballot_sync(FULL, amb)) {
+                // lane l only depends on lanes < l: after i rounds the first i lanes are final
+                ins = 0;
+                rem = 0;
+                while (true) {
+                    const int nl = n + __popc(ins & lt) - __popc(rem & lt);
+                    bool a2 = false;
+                    if (is_id) {
+                        const double p_make_bond = p_make_bond_raw / (double)(M - nl);  // sse.jl:164
+                        a2 = r < p_make_bond * w;                                        // sse.jl:166
+                    } else if (is_dg) {
+                        const double p_remove_bond = (double)(M - nl + 1) * p_remove_bond_raw;  // sse.jl:176-177
+                        a2 = r * w < p_remove_bond;                                              // sse.jl:178
+                    }
+                    const uint32_t ins2 = __ballot_sync(FULL, is_id && a2), rem2 = __ballot_sync(FULL, is_dg && a2);
+                    if (ins2 == ins && rem2 == rem) break;
+                    ins = ins2;
+                    rem = rem2;
                 }
-                const uint32_t ins2 = __ballot_sync(FULL, is_id && acc), rem2 = __ballot_sync(FULL, is_dg && acc);
-                if (ins2 == ins && rem2 == rem) break;
-                ins = ins2;
-                rem = rem2;
+            } else {
+                ins = __ballot_sync(FULL, is_id && acc);
+                rem = __ballot_sync(FULL, is_dg && acc);
             }
             n += __popc(ins) - __popc(rem);
             if (is_id && ((ins >> lane) & 1u)) newop = op_pack(bond, gvnew, 1u);
@@ -306,21 +395,30 @@ __device__ void phase_diag_build(const SmTab &st, const DevModel &dm, const DevW
             const uint32_t nm = __ballot_sync(FULL, nn);
             const uint32_t k = kbase + __popc(nm & lt);
             if ((long long)kbase + __popc(nm) > dw.n_cap) { c.flags |= SSE_FLAG_N_OVERFLOW; return; }
-            // nearest earlier / later operator of this chunk on each of my two sites
+            // same-site collisions inside the chunk are rare: every operator tags its two sites, a lost tag
+            // reveals a collision, and only then the nearest earlier / later operator on each site is searched
             uint32_t pa = NONE24, pb = NONE24, sua = NONE24, sub = NONE24;
-            for (uint32_t m = nm; m;) {
-                const int L = __ffs(m) - 1;
-                m &= m - 1;
-                const uint32_t qa = __shfl_sync(FULL, sa, L), qb = __shfl_sync(FULL, sb, L);
-                const uint32_t qk = __shfl_sync(FULL, k, L) << 2;
-                if (nn && (int)lane > L) {
-                    if (sa == qa) pa = qk | 2u;
-                    if (sa == qb) pa = qk | 3u;
-                    if (sb == qa) pb = qk | 2u;
-                    if (sb == qb) pb = qk | 3u;
-                } else if (nn && (int)lane < L) {
-                    if (sua == NONE24) { if (sa == qa) sua = qk; else if (sa == qb) sua = qk | 1u; }
-                    if (sub == NONE24) { if (sb == qa) sub = qk; else if (sb == qb) sub = qk | 1u; }
+            if (nn) {
+                c.mark[sa] = (uint8_t)lane;
+                c.mark[sb] = (uint8_t)lane;
+            }
+            __syncwarp();
+            const bool lost = nn && (c.mark[sa] != (uint8_t)lane || c.mark[sb] != (uint8_t)lane);
+            if (__ballot_sync(FULL, lost)) {
+                for (uint32_t m = nm; m;) {
+                    const int L = __ffs(m) - 1;
+                    m &= m - 1;
+                    const uint32_t qa = __shfl_sync(FULL, sa, L), qb = __shfl_sync(FULL, sb, L);
+                    const uint32_t qk = __shfl_sync(FULL, k, L) << 2;
+                    if (nn && (int)lane > L) {
+                        if (sa == qa) pa = qk | 2u;
+                        if (sa == qb) pa = qk | 3u;
+                        if (sb == qa) pb = qk | 2u;
+                        if (sb == qb) pb = qk | 3u;
+                    } else if (nn && (int)lane < L) {
+                        if (sua == NONE24) { if (sa == qa) sua = qk; else if (sa == qb) sua = qk | 1u; }
+                        if (sub == NONE24) { if (sb == qa) sub = qk; else if (sb == qb) sub = qk | 1u; }
+                    }
                 }
             }
             uint32_t ma = NONE32, mb = NONE32;
@@ -371,42 +469,44 @@ __device__ void phase_diag_build(const SmTab &st, const DevModel &dm, const DevW
 
 // ------------------------------------------------------------------------------------------------------
 // worm_traverse! inner loop (src/sse.jl:262-303) with scatter (src/vertex_data.jl:106-125).
-// All 32 lanes execute the chain uniformly; the lanes pre-compute the next 32 uniform draws in parallel.
+// All 32 lanes execute the chain uniformly; the lanes pre-compute the next 64 uniform draws in parallel
+// (one Philox block each) into the warp's shared scratch.
 // ------------------------------------------------------------------------------------------------------
 template <bool INJ>
-__device__ unsigned long long worm_traverse(const SmTab &st, const DevModel &dm, Ctx &c, const uint32_t k0,
-                                            const uint32_t l0, const uint32_t w0) {
-    const int maxw = dm.max_worm;
-    uint32_t k = k0, leg = l0, wf = w0;
-    unsigned long long len = 1;
-    unsigned long long base = c.draws;
-    double rbuf = sse_u01(draw<INJ>(c, base + c.lane));
-    uint32_t ri = 0;
+__device__ uint32_t worm_traverse(const SmTab &st, const DevModel &dm, Ctx &c, const uint32_t k0, const uint32_t l0,
+                                  const uint32_t w0) {
+    const uint32_t maxw = (uint32_t)dm.max_worm;
+    uint32_t k = k0, leg = l0, wf = w0, len = 1, fell = 0;
+    unsigned long long j0 = c.draws >> 1;
+    uint32_t ri = (uint32_t)(c.draws & 1ull);  // index into the scratch (draw 2*j0 + ri)
+    __syncwarp();
+    fill_draws<INJ>(c, j0);
+    __syncwarp();
     while (true) {
-        if (ri == 32) {
-            base += 32;
-            rbuf = sse_u01(draw<INJ>(c, base + c.lane));
+        if (ri == 64) {
+            j0 += 32;
             ri = 0;
+            __syncwarp();
+            fill_draws<INJ>(c, j0);
+            __syncwarp();
         }
-        const double r = shfl_f64(rbuf, ri);  // rand(rng) (sse.jl:282)
+        const double r = sse_u01(scratch_draw<INJ>(c, j0, 2ull * j0 + ri));  // rand(rng) (sse.jl:282)
         ++ri;
         const uint4 R = __ldcg(c.rec + k);
-        const uint32_t gv = op_gv(R.x);
-        const uint32_t t = st.trans[(gv * maxw + (wf - 1u)) * 4u + leg];  // transitions[leg_in, worm_in, vi]
-        const uint32_t off = t >> 10, cnt = t & 1023u;
-        uint32_t o = off;
-        uint4 e = st.outc[o];
-        bool hit = r < __hiloint2double((int)e.y, (int)e.x);
-        for (uint32_t j = 1; !hit && j < cnt; ++j) {  // first out with random < cumprob (vertex_data.jl:117-123)
-            o = off + j;
-            e = st.outc[o];
-            hit = r < __hiloint2double((int)e.y, (int)e.x);
+        // transitions[leg_in, worm_in, vi] fused with its first outcome (vertex_data.jl:115-123)
+        uint4 e = st.t1[(op_gv(R.x) * maxw + (wf - 1u)) * 4u + leg];
+        if (!(r < __hiloint2double((int)e.y, (int)e.x))) {
+            const uint32_t off = e.w >> 10, cnt = e.w & 1023u;
+            bool hit = false;
+            for (uint32_t j = 0; !hit && j < cnt; ++j) {  // first out with random < cumprob
+                e = st.outc[off + j];
+                hit = r < __hiloint2double((int)e.y, (int)e.x);
+            }
+            if (!hit) fell = 1;  // vertex_data.jl:124; clamped to the last outcome
         }
-        if (!hit) c.flags |= SSE_FLAG_SCATTER_FALLTHROUGH;  // vertex_data.jl:124; clamped to the last outcome
         const uint32_t pk = e.z;
         const uint32_t leg_out = (pk >> 13) & 3u, w_out = (pk >> 15) & 0xffu, dim_out = (pk >> 23) & 0xffu;
-        const uint32_t newop = (R.x & ~(VMASK | 2u)) | ((pk & 0x1fffu) << 1);  // OperCode(bond, new_vertex) (sse.jl:285)
-        reinterpret_cast<uint32_t *>(c.rec + k)[0] = newop;
+        reinterpret_cast<uint32_t *>(c.rec + k)[0] = (R.x & ~(VMASK | 2u)) | ((pk & 0x1fffu) << 1);  // OperCode(bond, new_vertex) (sse.jl:285)
         if (k == k0 && leg_out == l0 && w_out == dim_out - w0) break;  // sse.jl:288-290
         ++len;
         wf = w_out;
@@ -415,7 +515,8 @@ __device__ unsigned long long worm_traverse(const SmTab &st, const DevModel &dm,
         leg = lk & 3u;
         if (k == k0 && leg == l0 && wf == w0) break;  // sse.jl:297-299
     }
-    c.draws = base + ri;
+    c.draws = 2ull * j0 + ri;
+    if (fell) c.flags |= SSE_FLAG_SCATTER_FALLTHROUGH;
     if (INJ && (long long)c.draws > c.inj_len) c.flags |= SSE_FLAG_STREAM_EXHAUSTED;
     return len;
 }
@@ -455,7 +556,7 @@ __device__ void phase_worm_update(const SmTab &st, const DevModel &dm, const Dev
         const uint32_t dim0 = (l0 & 1u) ? (bi.y >> 24) : (bi.x >> 24);  // site_of_leg (sse.jl:250)
         const uint32_t w0 = 1u + (uint32_t)sse_uint_below(draw<INJ>(c, c.draws), dim0 - 1u);  // sse.jl:251
         c.draws += 1;
-        const unsigned long long len = worm_traverse<INJ>(st, dm, c, k0, l0, w0);
+        const uint32_t len = worm_traverse<INJ>(st, dm, c, k0, l0, w0);
         total += (double)len;
         c.visits += len;
         if (c.flags & SSE_FLAG_STREAM_EXHAUSTED) return;
@@ -479,6 +580,7 @@ __device__ void phase_worm_update(const SmTab &st, const DevModel &dm, const Dev
     }
     // rebuild the state from the first leg on each site; untouched sites are redrawn IN SITE ORDER (sse.jl:219-228)
     const int N = dm.n_sites;
+    __syncwarp();
     for (int b = 0; b < N; b += 32) {
         const int s = b + (int)lane;
         const bool act = s < N;
@@ -554,11 +656,14 @@ __device__ void phase_commit_measure(const SmTab &st, const DevModel &dm, const 
                 delta = (__ldg(ea + ((vi >> 16) & 0xffu) - 1) - __ldg(ea + (vi & 0xffu) - 1)) +
                         (__ldg(eb + (vi >> 24) - 1) - __ldg(eb + ((vi >> 8) & 0xffu) - 1));
             }
+            const uint32_t offm = __ballot_sync(FULL, delta != 0.0);
             double scan = delta;  // inclusive prefix sum over the chunk, in slot order
+            if (offm) {
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const double up = shfl_up_f64(scan, d);
-                if ((int)lane >= d) scan += up;
+                for (int d = 1; d < 32; d <<= 1) {
+                    const double up = shfl_up_f64(scan, d);
+                    if ((int)lane >= d) scan += up;
+                }
             }
             if (nonid) {  // every non-identity operator is one sample (:152-158)
                 const double v = tmpmag + scan, v2 = v * v;
@@ -567,7 +672,7 @@ __device__ void phase_commit_measure(const SmTab &st, const DevModel &dm, const 
                 mag2 += v2;
                 mag4 += v2 * v2;
             }
-            tmpmag += shfl_f64(scan, 31);
+            if (offm) tmpmag += shfl_f64(scan, 31);
         }
         mag = warp_sum_f64(mag);
         absmag = warp_sum_f64(absmag);
@@ -598,13 +703,20 @@ __device__ __forceinline__ SmTab stage_tables(const DevModel &dm, uint8_t *smem)
     for (int i = threadIdx.x; i < n16; i += blockDim.x) dst[i] = __ldg(src + i);
     __syncthreads();
     SmTab st;
+    st.t1 = reinterpret_cast<const uint4 *>(smem + dm.tl.off_t1);
     st.outc = reinterpret_cast<const uint4 *>(smem + dm.tl.off_outc);
     st.weights = reinterpret_cast<const double *>(smem + dm.tl.off_weights);
-    st.trans = reinterpret_cast<const uint32_t *>(smem + dm.tl.off_trans);
     st.vinfo = reinterpret_cast<const uint32_t *>(smem + dm.tl.off_vinfo);
     st.diagv = reinterpret_cast<const uint16_t *>(smem + dm.tl.off_diagv);
     st.vneg = reinterpret_cast<const uint8_t *>(smem + dm.tl.off_vneg);
     return st;
+}
+
+// bytes of per-warp shared scratch: random draws + (optionally) state[N] and mark[N]
+__host__ __device__ inline int warp_scratch_bytes(int n_sites, int smem_state) {
+    int b = RNG_WORDS * 8;
+    if (smem_state) b += 2 * ((n_sites + 15) & ~15);
+    return (b + 15) & ~15;
 }
 
 // The one kernel: every mode shares the phase code above.  One warp = one walker.
@@ -612,15 +724,26 @@ template <bool INJ>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 7) k_walkers(const DevModel dm, const DevWalkers dw, const LaunchArgs a) {
     extern __shared__ __align__(16) uint8_t smem[];
     const SmTab st = stage_tables(dm, smem);
-    const int w = blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5);
+    const int warp = threadIdx.x >> 5;
+    const int w = blockIdx.x * WARPS_PER_CTA + warp;
     if (w >= dw.W) return;
+    const int N = dm.n_sites;
     Ctx c;
     c.lane = threadIdx.x & 31;
+    uint8_t *scratch = smem + dm.tl.bytes + (size_t)warp * warp_scratch_bytes(N, dw.smem_state);
+    c.rng = reinterpret_cast<unsigned long long *>(scratch);
+    uint8_t *gstate = dw.state + (size_t)w * N;
+    if (dw.smem_state) {
+        c.state = scratch + RNG_WORDS * 8;
+        c.mark = c.state + ((N + 15) & ~15);
+    } else {
+        c.state = gstate;
+        c.mark = dw.mark + (size_t)w * N;
+    }
     c.ops = dw.ops + (size_t)w * dw.M_cap;
     c.rec = dw.rec + (size_t)w * dw.n_cap;
-    c.state = dw.state + (size_t)w * dm.n_sites;
-    c.vfirst = dw.vfirst + (size_t)w * dm.n_sites;
-    c.vlast = dw.vlast + (size_t)w * dm.n_sites;
+    c.vfirst = dw.vfirst + (size_t)w * N;
+    c.vlast = dw.vlast + (size_t)w * N;
     c.inj = INJ ? dw.inj + (size_t)w * dw.inj_len : nullptr;
     c.inj_len = dw.inj_len;
     c.seed = dw.seed;
@@ -636,6 +759,11 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 7) k_walkers(const DevMode
     c.visits = 0;
     const uint32_t fatal = SSE_FLAG_M_OVERFLOW | SSE_FLAG_N_OVERFLOW | SSE_FLAG_STREAM_EXHAUSTED;
     if (c.flags & fatal) return;
+    for (int s = c.lane; s < N; s += 32) {
+        if (dw.smem_state) c.state[s] = gstate[s];
+        c.mark[s] = 0;
+    }
+    __syncwarp();
     double *out = dw.obs_out + (size_t)w * dw.n_obs;
     unsigned long long sweeps = 0, sum_n = 0, sum_M = 0;
 
@@ -660,9 +788,9 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 7) k_walkers(const DevMode
             }
             break;
         case MODE_INIT: {  // Carlo.init! (sse.jl:47-60): M and the zeroed string are set by the host
-            for (int s = c.lane; s < dm.n_sites; s += 32)
+            for (int s = c.lane; s < N; s += 32)
                 c.state[s] = (uint8_t)(1u + (uint32_t)sse_uint_below(draw<INJ>(c, c.draws + s), dm.site_dim[s]));
-            c.draws += dm.n_sites;
+            c.draws += N;
             __syncwarp();
             for (int i = 0; i < a.warmup && !(c.flags & fatal); ++i) phase_diag_build<INJ>(st, dm, dw, c, true, false);
             break;
@@ -691,6 +819,9 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 7) k_walkers(const DevMode
             break;
     }
     if (INJ && (long long)c.draws > c.inj_len) c.flags |= SSE_FLAG_STREAM_EXHAUSTED;
+    __syncwarp();
+    if (dw.smem_state)
+        for (int s = c.lane; s < N; s += 32) gstate[s] = c.state[s];
     if (c.lane == 0) {
         dw.draws[w] = c.draws;
         dw.num_worms[w] = c.num_worms;

@@ -115,15 +115,16 @@ def test_injected_stream_equals_philox_stream():
 
 
 def _philox(seed, walker, k):
-    """Pure-Python Philox4x32-10 low 64 bits (include/sse_rng.h)."""
+    """Pure-Python draw k of the Philox stream (include/sse_rng.h): block k>>1, word pair k&1."""
     M0, M1, W0, W1, mask = 0xD2511F53, 0xCD9E8D57, 0x9E3779B9, 0xBB67AE85, 0xFFFFFFFF
-    c = [k & mask, (k >> 32) & mask, walker & mask, (walker >> 32) & mask]
+    j, half = k >> 1, k & 1
+    c = [j & mask, (j >> 32) & mask, walker & mask, (walker >> 32) & mask]
     k0, k1 = seed & mask, (seed >> 32) & mask
     for _ in range(10):
         p0, p1 = M0 * c[0], M1 * c[2]
         c = [(p1 >> 32) ^ c[1] ^ k0, p1 & mask, (p0 >> 32) ^ c[3] ^ k1, p0 & mask]
         k0, k1 = (k0 + W0) & mask, (k1 + W1) & mask
-    return c[0] | (c[1] << 32)
+    return (c[2] | (c[3] << 32)) if half else (c[0] | (c[1] << 32))
 
 
 def test_philox_known_answer():
@@ -140,6 +141,7 @@ def test_philox_known_answer():
     f = 0xFFFFFFFF
     assert block([f, f, f, f], (f, f)) == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
     assert _philox(0, 0, 0) == 0x6627e8d5 | (0xe169c58d << 32)
+    assert _philox(0, 0, 1) == 0xbc57ac4c | (0x9b00dbd8 << 32)
 
 
 ED_JOBS = {
