@@ -296,6 +296,8 @@ def run_ours(args):
                     "api": "sse_set_temperature + sse_sweep(measure=1) + sse_fetch_accumulators per step",
                     "energy_per_site": energy},
             "gpu_launches": args.steps,
+            "phase_cycle_share": {k: cnt[k] / max(1, cnt["cycles_diag_build"] + cnt["cycles_worm"] + cnt["cycles_commit_measure"])
+                                  for k in ("cycles_diag_build", "cycles_worm", "cycles_commit_measure")},
             "clocks": clocks,
             "setup_s": t_setup,
         }

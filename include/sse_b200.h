@@ -148,9 +148,10 @@ int32_t sse_fetch_accumulators(sse_walkers *w, double *sums, int64_t *counts, in
 /* Device pointers of the same buffers, for NCCL reductions by the host (no copy). */
 int32_t sse_accumulators_device_ptr(sse_walkers *w, void **sums, void **counts);
 
-/* Totals since creation or the last reset: worm-vertex visits (sum of worm_traverse! lengths,
- * src/sse.jl:302), walker-sweeps, non-identity operators and string slots summed over sweeps. */
-int32_t sse_fetch_counters(sse_walkers *w, uint64_t out[4], int32_t reset);
+/* Totals since creation or the last reset: [0] worm-vertex visits (sum of worm_traverse! lengths,
+ * src/sse.jl:302), [1] walker-sweeps, [2] non-identity operators and [3] string slots summed over sweeps,
+ * [4..6] SM cycles spent in diagonal-update+vertex-list / worm update / commit+measure summed over walkers, [7] spare. */
+int32_t sse_fetch_counters(sse_walkers *w, uint64_t out[8], int32_t reset);
 
 /* Carlo.write_checkpoint / read_checkpoint (src/sse.jl:89-107). */
 int32_t sse_get_state(sse_walkers *w, int32_t walker, sse_walker_state *st);

@@ -207,13 +207,13 @@ int32_t sse_model_create(const sse_model_desc *d, sse_model **out) {
     for (int i = 0; i < n_trans; ++i) {
         int o = d->trans_offset[i], c = d->trans_count[i];
         if (o < 0) continue;
-        if (c < 1 || c > 1023 || o + c > n_out || o >= (1 << 22)) { delete m; return fail("sse_model_create: bad transition entry"); }
+        if (c < 1 || c > 64 || o + c > n_out || o + 1 >= (1 << 18)) { delete m; return fail("sse_model_create: bad transition entry (at most 64 outcomes per transition, 2^18 outcomes in total)"); }
         int v = i / (d->max_worm * 4);
         for (int j = 0; j < c; ++j) otype[o + j] = vtype[v];
     }
     for (int o = 0; o < n_out; ++o) {
         int t = otype[o];
-        uint32_t pk = 0;
+        uint32_t pk = 0, pw = 0;
         if (t >= 0) {
             int tv = d->out_target[o];
             int leg = d->out_leg[o], worm = d->out_worm[o];
@@ -223,19 +223,19 @@ int32_t sse_model_create(const sse_model_desc *d, sse_model **out) {
                 return fail("sse_model_create: bad outcome entry");
             }
             int dim_out = d->type_dims[2 * t + (leg & 1)];
-            pk = (uint32_t)m->is_diag[gv] | ((uint32_t)gv << 1) | ((uint32_t)leg << 13) | ((uint32_t)worm << 15) |
-                 ((uint32_t)dim_out << 23);
+            pk = ((uint32_t)m->is_diag[gv] << 1) | ((uint32_t)gv << 2) | ((uint32_t)leg << 16) | ((uint32_t)worm << 24);
+            pw = (uint32_t)dim_out << 24;
         }
         uint64_t bits;
         double cp = d->out_cumprob[o];
         memcpy(&bits, &cp, 8);
-        outc[o] = make_uint4((uint32_t)bits, (uint32_t)(bits >> 32), pk, 0u);
+        outc[o] = make_uint4((uint32_t)bits, (uint32_t)(bits >> 32), pk, pw);
     }
     // transition header fused with its first outcome; invalid transitions get cumprob +inf and step 0
     for (int i = 0; i < n_trans; ++i) {
         int o = d->trans_offset[i], c = d->trans_count[i];
         if (o < 0) { t1[i] = make_uint4(0u, 0x7ff00000u, 0u, 0u); continue; }
-        t1[i] = make_uint4(outc[o].x, outc[o].y, outc[o].z, ((uint32_t)(o + 1) << 10) | (uint32_t)(c - 1));
+        t1[i] = make_uint4(outc[o].x, outc[o].y, outc[o].z, outc[o].w | ((uint32_t)(o + 1) << 6) | (uint32_t)(c - 1));
     }
     CU(upload(&m->d_bond_info, bi));
     CU(upload(&m->d_site_dim, m->site_dim));
@@ -291,7 +291,10 @@ int32_t sse_walkers_create(const sse_model *m, const sse_walkers_opts *o, sse_wa
     s |= dev_alloc(w, &dw.rec, (size_t)W * dw.n_cap, false);
     s |= dev_alloc(w, &dw.state, (size_t)W * N, false);
     // per-warp state[N] + mark[N] live in shared memory when 7 CTAs/SM still fit, else in global scratch
-    dw.smem_state = (m->dm.tl.bytes + WARPS_PER_CTA * warp_scratch_bytes(N, 1) <= 99 * 1024) ? 1 : 0;
+    // level 2 (+ vlast) only while 7 CTAs/SM still fit (32 KB per CTA); level 1 up to 99 KB per CTA
+    dw.smem_state = 0;
+    if (m->dm.tl.bytes + WARPS_PER_CTA * warp_scratch_bytes(N, 1) <= 99 * 1024) dw.smem_state = 1;
+    if (m->dm.tl.bytes + WARPS_PER_CTA * warp_scratch_bytes(N, 2) <= 32 * 1024) dw.smem_state = 2;
     if (!dw.smem_state) s |= dev_alloc(w, &dw.mark, (size_t)W * N, true);
     s |= dev_alloc(w, &dw.vfirst, (size_t)W * N, false);
     s |= dev_alloc(w, &dw.vlast, (size_t)W * N, false);
@@ -305,7 +308,7 @@ int32_t sse_walkers_create(const sse_model *m, const sse_walkers_opts *o, sse_wa
     s |= dev_alloc(w, &dw.flags, W, true);
     s |= dev_alloc(w, &dw.acc, (size_t)W * dw.n_obs, true);
     s |= dev_alloc(w, &dw.acc_cnt, (size_t)W * 2, true);
-    s |= dev_alloc(w, &dw.counters, 4, true);
+    s |= dev_alloc(w, &dw.counters, 8, true);
     s |= dev_alloc(w, &dw.dbg_len, W, true);
     s |= dev_alloc(w, &dw.obs_out, (size_t)W * dw.n_obs, true);
     if (s) { sse_walkers_destroy(w); return 1; }
@@ -426,10 +429,10 @@ int32_t sse_accumulators_device_ptr(sse_walkers *w, void **sums, void **counts) 
     return 0;
 }
 
-int32_t sse_fetch_counters(sse_walkers *w, uint64_t out[4], int32_t reset) {
+int32_t sse_fetch_counters(sse_walkers *w, uint64_t out[8], int32_t reset) {
     if (!w || !out) return fail("null argument");
-    CU(cudaMemcpyAsync(out, w->dw.counters, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost, w->stream));
-    if (reset) CU(cudaMemsetAsync(w->dw.counters, 0, 4 * sizeof(uint64_t), w->stream));
+    CU(cudaMemcpyAsync(out, w->dw.counters, 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost, w->stream));
+    if (reset) CU(cudaMemsetAsync(w->dw.counters, 0, 8 * sizeof(uint64_t), w->stream));
     CU(cudaStreamSynchronize(w->stream));
     return 0;
 }

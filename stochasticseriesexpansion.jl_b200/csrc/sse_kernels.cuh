@@ -50,15 +50,14 @@ __host__ __device__ __forceinline__ uint32_t op_bond(uint32_t op) { return op >>
 struct TabLayout {
     int bytes;
     int off_t1;       // uint4  [nv*max_worm*4] first outcome fused with the transition header:
-                      //        {cumprob0 lo, cumprob0 hi, packed step0, (offset of outcome 1 << 10) | remaining count}
-    int off_outc;     // uint4  [n_outcomes] {cumprob lo, cumprob hi, packed step, 0}
+                      //        {cumprob0 lo, cumprob0 hi, packed step0, dim_out << 24 | offset of outcome 1 << 6 | remaining count}
+    int off_outc;     // uint4  [n_outcomes] {cumprob lo, cumprob hi, packed step, dim_out << 24}
     int off_weights;  // double [nv]
     int off_vinfo;    // u32    [nv]  leg states packed, 8 bits per leg
     int off_diagv;    // u16    [n_diag]  global vertex id + 1, 0 = invalid
     int off_vneg;     // u8     [nv]  1 if the vertex sign is negative
 };
-// packed step: bit0 = diagonal flag of the target, bits 1..12 = target gv, bits 13..14 = exit leg,
-//              bits 15..22 = exit worm, bits 23..30 = dim of the exit leg's site
+// packed step: see worm_traverse_loop
 struct SmTab {
     const uint4 *t1;
     const uint4 *outc;
@@ -93,7 +92,7 @@ struct DevWalkers {
     uint32_t *flags;
     double *acc;                 // [W][n_obs]
     long long *acc_cnt;          // [W][2]
-    unsigned long long *counters;// [4] visits, walker-sweeps, sum n, sum M
+    unsigned long long *counters;// [8] visits, walker-sweeps, sum n, sum M, cycles in K1K2 / K3 / K4C, spare
     long long *dbg_len;          // [W] worm length of the last sse_dbg_worm_traverse
     double *obs_out;             // [W][n_obs] scratch for sse_measure
     const unsigned long long *inj;
@@ -101,7 +100,7 @@ struct DevWalkers {
     unsigned long long seed, wid_off;
     double twlf, atten;
     int n_obs;
-    int smem_state;              // 1: state/mark arrays live in shared memory
+    int smem_state;              // per-warp arrays in shared memory: 0 none, 1 state+mark, 2 state+mark+vlast
 };
 
 enum Mode : int {
@@ -403,9 +402,15 @@ __device__ void phase_diag_build(const SmTab &st, const DevModel &dm, const DevW
                 c.mark[sb] = (uint8_t)lane;
             }
             __syncwarp();
-            const bool lost = nn && (c.mark[sa] != (uint8_t)lane || c.mark[sb] != (uint8_t)lane);
-            if (__ballot_sync(FULL, lost)) {
-                for (uint32_t m = nm; m;) {
+            const bool lost_a = nn && c.mark[sa] != (uint8_t)lane, lost_b = nn && c.mark[sb] != (uint8_t)lane;
+            if (__ballot_sync(FULL, lost_a || lost_b)) {
+                // losers flag the contested sites; every operator on a flagged site takes part in the search
+                __syncwarp();
+                if (lost_a) c.mark[sa] = 0x7f;
+                if (lost_b) c.mark[sb] = 0x7f;
+                __syncwarp();
+                const bool inv = nn && (c.mark[sa] == 0x7f || c.mark[sb] == 0x7f);
+                for (uint32_t m = __ballot_sync(FULL, inv); m;) {
                     const int L = __ffs(m) - 1;
                     m &= m - 1;
                     const uint32_t qa = __shfl_sync(FULL, sa, L), qb = __shfl_sync(FULL, sb, L);
@@ -470,53 +475,144 @@ __device__ void phase_diag_build(const SmTab &st, const DevModel &dm, const DevW
 // ------------------------------------------------------------------------------------------------------
 // worm_traverse! inner loop (src/sse.jl:262-303) with scatter (src/vertex_data.jl:106-125).
 // All 32 lanes execute the chain uniformly; the lanes pre-compute the next 64 uniform draws in parallel
-// (one Philox block each) into the warp's shared scratch.
+// (one Philox block each) into the warp's shared scratch.  Kept out of line with a minimal argument set so
+// the chase loop owns its registers: per visit one 16 B global load, one 16 B shared load, one f64 compare,
+// one 4 B store.
 // ------------------------------------------------------------------------------------------------------
+struct WormArgs {
+    uint4 *rec;
+    uint32_t t1_s, outc_s, rbuf_s;  // shared-space addresses
+    const unsigned long long *inj;
+    long long inj_len;
+    unsigned long long seed, wid, draws;
+    uint32_t maxw, lane, k0, l0, w0, fell;
+};
+
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ double lds_f64(uint32_t a) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts_f64x2(uint32_t a, double x, double y) {
+    asm volatile("st.shared.v2.f64 [%0], {%1,%2};" ::"r"(a), "d"(x), "d"(y) : "memory");
+}
+
+// uniform doubles for the draws [2*j0, 2*j0 + 64) -> rbuf[64]
 template <bool INJ>
-__device__ uint32_t worm_traverse(const SmTab &st, const DevModel &dm, Ctx &c, const uint32_t k0, const uint32_t l0,
-                                  const uint32_t w0) {
-    const uint32_t maxw = (uint32_t)dm.max_worm;
-    uint32_t k = k0, leg = l0, wf = w0, len = 1, fell = 0;
-    unsigned long long j0 = c.draws >> 1;
-    uint32_t ri = (uint32_t)(c.draws & 1ull);  // index into the scratch (draw 2*j0 + ri)
-    __syncwarp();
-    fill_draws<INJ>(c, j0);
-    __syncwarp();
-    while (true) {
-        if (ri == 64) {
-            j0 += 32;
-            ri = 0;
-            __syncwarp();
-            fill_draws<INJ>(c, j0);
-            __syncwarp();
-        }
-        const double r = sse_u01(scratch_draw<INJ>(c, j0, 2ull * j0 + ri));  // rand(rng) (sse.jl:282)
-        ++ri;
-        const uint4 R = __ldcg(c.rec + k);
-        // transitions[leg_in, worm_in, vi] fused with its first outcome (vertex_data.jl:115-123)
-        uint4 e = st.t1[(op_gv(R.x) * maxw + (wf - 1u)) * 4u + leg];
-        if (!(r < __hiloint2double((int)e.y, (int)e.x))) {
-            const uint32_t off = e.w >> 10, cnt = e.w & 1023u;
-            bool hit = false;
-            for (uint32_t j = 0; !hit && j < cnt; ++j) {  // first out with random < cumprob
-                e = st.outc[off + j];
-                hit = r < __hiloint2double((int)e.y, (int)e.x);
-            }
-            if (!hit) fell = 1;  // vertex_data.jl:124; clamped to the last outcome
-        }
-        const uint32_t pk = e.z;
-        const uint32_t leg_out = (pk >> 13) & 3u, w_out = (pk >> 15) & 0xffu, dim_out = (pk >> 23) & 0xffu;
-        reinterpret_cast<uint32_t *>(c.rec + k)[0] = (R.x & ~(VMASK | 2u)) | ((pk & 0x1fffu) << 1);  // OperCode(bond, new_vertex) (sse.jl:285)
-        if (k == k0 && leg_out == l0 && w_out == dim_out - w0) break;  // sse.jl:288-290
-        ++len;
-        wf = w_out;
-        const uint32_t lk = rec_link(R, leg_out);  // (leg_in, p) = vertices[leg_out, p] (sse.jl:295)
-        k = lk >> 2;
-        leg = lk & 3u;
-        if (k == k0 && leg == l0 && wf == w0) break;  // sse.jl:297-299
+__device__ __forceinline__ void fill_u01(const WormArgs &a, unsigned long long j0) {
+    uint64_t x0, x1;
+    if (INJ) {
+        const unsigned long long k = 2ull * (j0 + a.lane);
+        x0 = (long long)k < a.inj_len ? (uint64_t)__ldg(a.inj + k) : 0ull;
+        x1 = (long long)(k + 1) < a.inj_len ? (uint64_t)__ldg(a.inj + k + 1) : 0ull;
+    } else {
+        uint32_t b[4];
+        sse_philox_block(a.seed, a.wid, j0 + a.lane, b);
+        x0 = (uint64_t)b[0] | ((uint64_t)b[1] << 32);
+        x1 = (uint64_t)b[2] | ((uint64_t)b[3] << 32);
     }
-    c.draws = 2ull * j0 + ri;
-    if (fell) c.flags |= SSE_FLAG_SCATTER_FALLTHROUGH;
+    sts_f64x2(a.rbuf_s + 16u * a.lane, sse_u01(x0), sse_u01(x1));
+}
+
+__device__ __forceinline__ uint4 ldg_cg128(const uint4 *p) {
+    uint4 v;
+    asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void stg_u32(void *p, uint32_t v) {
+    asm volatile("st.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// packed step (t1[].z / outc[].z): bits 1..13 = vertex bits of the op code (diag << 1 | gv << 2),
+// bits 16..17 = exit leg, bits 24..31 = exit worm;  .w: bits 24..31 = dim of the exit leg's site,
+// (t1 only) bits 6..23 = offset of the 2nd outcome, bits 0..5 = number of further outcomes.
+template <bool INJ>
+__device__ __noinline__ uint32_t worm_traverse_loop(WormArgs &a) {
+    uint4 *const rec = a.rec;
+    const uint32_t t1_s = a.t1_s, outc_s = a.outc_s, rbuf_s = a.rbuf_s, maxw4 = a.maxw * 4u;
+    const uint32_t pos0 = (a.k0 << 2) | a.l0, w0 = a.w0;
+    uint32_t pos = pos0, wf = w0, len = 1, fell = 0;
+    unsigned long long j0 = a.draws >> 1;
+    uint32_t ri = (uint32_t)(a.draws & 1ull);  // index into rbuf (draw 2*j0 + ri)
+    uint4 R = ldg_cg128(rec + (pos >> 2));
+    bool done = false;
+    while (true) {
+        __syncwarp();
+        fill_u01<INJ>(a, j0);
+        __syncwarp();
+        while (ri < 64) {
+            const double r = lds_f64(rbuf_s + 8u * ri);  // rand(rng) (sse.jl:282)
+            ++ri;
+            // transitions[leg_in, worm_in, vi] fused with its first outcome (vertex_data.jl:115-123)
+            uint4 e = lds128(t1_s + 16u * (op_gv(R.x) * maxw4 + (((wf - 1u) << 2) | (pos & 3u))));
+            // The first outcome is by far the most likely: follow its link SPECULATIVELY so the next record's
+            // load is in flight while the compare, the store and the stop tests of this visit execute.
+            uint32_t leg_out = (e.z >> 16) & 3u;
+            uint32_t posn = rec_link(R, leg_out);  // (leg_in, p) = vertices[leg_out, p] (sse.jl:295)
+            const uint4 Rs = ldg_cg128(rec + (posn >> 2));
+            uint4 Rn;
+            if (r < __hiloint2double((int)e.y, (int)e.x)) {
+                Rn = Rs;
+            } else {
+                const uint32_t off = (e.w >> 6) & 0x3ffffu, cnt = e.w & 63u;
+                bool hit = false;
+                for (uint32_t j = 0; !hit && j < cnt; ++j) {  // first out with random < cumprob
+                    e = lds128(outc_s + 16u * (off + j));
+                    hit = r < __hiloint2double((int)e.y, (int)e.x);
+                }
+                if (!hit) fell = 1;  // vertex_data.jl:124; clamped to the last outcome
+                leg_out = (e.z >> 16) & 3u;
+                posn = rec_link(R, leg_out);
+                Rn = ldg_cg128(rec + (posn >> 2));  // issued while the mispredicted load is still in flight
+                asm volatile("" ::"r"(Rs.x), "r"(Rs.y), "r"(Rs.z), "r"(Rs.w));  // keep Rs in its own registers (no WAW wait)
+            }
+            const uint32_t w_out = e.z >> 24, dim_out = e.w >> 24;
+            const uint32_t newop = (R.x & ~(VMASK | 2u)) | (e.z & (VMASK | 2u));  // OperCode(bond, new_vertex) (sse.jl:285)
+            stg_u32(rec + (pos >> 2), newop);
+            if (((pos & ~3u) | leg_out) == pos0 && w_out + w0 == dim_out) { done = true; break; }  // sse.jl:288-290
+            ++len;
+            wf = w_out;
+            if ((posn >> 2) == (pos >> 2)) Rn.x = newop;  // the link re-enters this record: its load preceded the store
+            pos = posn;
+            R = Rn;
+            if (pos == pos0 && wf == w0) { done = true; break; }  // sse.jl:297-299
+        }
+        if (done) break;
+        j0 += 32;
+        ri = 0;
+    }
+    a.draws = 2ull * j0 + ri;
+    a.fell = fell;
+    return len;
+}
+
+template <bool INJ>
+__device__ __forceinline__ uint32_t worm_traverse(const SmTab &st, const DevModel &dm, Ctx &c, const uint32_t k0,
+                                                  const uint32_t l0, const uint32_t w0) {
+    WormArgs a;
+    a.rec = c.rec;
+    a.t1_s = (uint32_t)__cvta_generic_to_shared(st.t1);
+    a.outc_s = (uint32_t)__cvta_generic_to_shared(st.outc);
+    a.rbuf_s = (uint32_t)__cvta_generic_to_shared(c.rng);
+    a.inj = c.inj;
+    a.inj_len = c.inj_len;
+    a.seed = c.seed;
+    a.wid = c.wid;
+    a.draws = c.draws;
+    a.maxw = (uint32_t)dm.max_worm;
+    a.lane = c.lane;
+    a.k0 = k0;
+    a.l0 = l0;
+    a.w0 = w0;
+    a.fell = 0;
+    const uint32_t len = worm_traverse_loop<INJ>(a);
+    c.draws = a.draws;
+    if (a.fell) c.flags |= SSE_FLAG_SCATTER_FALLTHROUGH;
     if (INJ && (long long)c.draws > c.inj_len) c.flags |= SSE_FLAG_STREAM_EXHAUSTED;
     return len;
 }
@@ -712,10 +808,11 @@ __device__ __forceinline__ SmTab stage_tables(const DevModel &dm, uint8_t *smem)
     return st;
 }
 
-// bytes of per-warp shared scratch: random draws + (optionally) state[N] and mark[N]
-__host__ __device__ inline int warp_scratch_bytes(int n_sites, int smem_state) {
+// bytes of per-warp shared scratch: random draws + (level >= 1) state[N], mark[N] + (level 2) vlast[N]
+__host__ __device__ inline int warp_scratch_bytes(int n_sites, int level) {
     int b = RNG_WORDS * 8;
-    if (smem_state) b += 2 * ((n_sites + 15) & ~15);
+    if (level >= 1) b += 2 * ((n_sites + 15) & ~15);
+    if (level >= 2) b += 4 * ((n_sites + 3) & ~3);
     return (b + 15) & ~15;
 }
 
@@ -743,7 +840,8 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 7) k_walkers(const DevMode
     c.ops = dw.ops + (size_t)w * dw.M_cap;
     c.rec = dw.rec + (size_t)w * dw.n_cap;
     c.vfirst = dw.vfirst + (size_t)w * N;
-    c.vlast = dw.vlast + (size_t)w * N;
+    uint32_t *gvlast = dw.vlast + (size_t)w * N;
+    c.vlast = dw.smem_state >= 2 ? reinterpret_cast<uint32_t *>(c.mark + ((N + 15) & ~15)) : gvlast;
     c.inj = INJ ? dw.inj + (size_t)w * dw.inj_len : nullptr;
     c.inj_len = dw.inj_len;
     c.seed = dw.seed;
@@ -765,16 +863,23 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 7) k_walkers(const DevMode
     }
     __syncwarp();
     double *out = dw.obs_out + (size_t)w * dw.n_obs;
-    unsigned long long sweeps = 0, sum_n = 0, sum_M = 0;
+    unsigned long long sweeps = 0, sum_n = 0, sum_M = 0, cyc[3] = {0, 0, 0};
 
     switch (a.mode) {
         case MODE_SWEEP:
             for (int s = 0; s < a.n_sweeps && !(c.flags & fatal); ++s) {  // Carlo.sweep! (sse.jl:62-68)
+                const long long t0 = clock64();
                 phase_diag_build<INJ>(st, dm, dw, c, true, true);
                 if (c.flags & fatal) break;
+                const long long t1 = clock64();
                 phase_worm_update<INJ>(st, dm, dw, c, a.thermalized != 0, w);
                 if (c.flags & fatal) break;
+                const long long t2 = clock64();
                 phase_commit_measure(st, dm, dw, c, true, a.measure != 0, out);
+                const long long t3 = clock64();
+                cyc[0] += (unsigned long long)(t1 - t0);
+                cyc[1] += (unsigned long long)(t2 - t1);
+                cyc[2] += (unsigned long long)(t3 - t2);
                 ++sweeps;
                 sum_n += (unsigned long long)c.n;
                 sum_M += (unsigned long long)c.M;
@@ -822,6 +927,8 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 7) k_walkers(const DevMode
     __syncwarp();
     if (dw.smem_state)
         for (int s = c.lane; s < N; s += 32) gstate[s] = c.state[s];
+    if (dw.smem_state >= 2 && (a.mode == MODE_MAKE_VL))
+        for (int s = c.lane; s < N; s += 32) gvlast[s] = c.vlast[s];  // read back by sse_dbg_get_vertex_list
     if (c.lane == 0) {
         dw.draws[w] = c.draws;
         dw.num_worms[w] = c.num_worms;
@@ -835,6 +942,9 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 7) k_walkers(const DevMode
             atomicAdd(dw.counters + 1, sweeps);
             atomicAdd(dw.counters + 2, sum_n);
             atomicAdd(dw.counters + 3, sum_M);
+            atomicAdd(dw.counters + 4, cyc[0]);  // SM cycles spent per phase, summed over walkers
+            atomicAdd(dw.counters + 5, cyc[1]);
+            atomicAdd(dw.counters + 6, cyc[2]);
         }
     }
 }

@@ -14,9 +14,28 @@ from . import estimators as _est
 from .walkers import OBS_FIXED, DeviceModel, Walkers
 
 
-def default_capacity(n_sites: int, n_bonds: int, T_min: float) -> int:
-    """Heuristic string capacity: generous multiple of the expected operator count n ~ N_b * |e_b| / T."""
-    return int(max(4096, 6.0 * n_bonds / T_min + 4 * n_sites + 1024))
+def operator_count_bound(sse_data, T_min: float) -> float:
+    """Upper bound on the mean operator count: <n> = beta * sum_b <eps_b - H_b> <= beta * sum_b lambda_max(eps_b - H_b).
+    The shifted bond operator is rebuilt from the vertex table (weights with signs between leg states)."""
+    lam = []
+    for vd in sse_data.vertex_data:
+        d0, d1 = vd.dims
+        Wm = np.zeros((d0 * d1, d0 * d1))
+        ls = vd.leg_states.astype(np.int64) - 1
+        rows = ls[0] + d0 * ls[1]
+        cols = ls[2] + d0 * ls[3]
+        Wm[rows, cols] = vd.weights * vd.signs
+        lam.append(float(np.linalg.eigvalsh(0.5 * (Wm + Wm.T)).max()))
+    total = sum(lam[b.type - 1] for b in sse_data.bonds)
+    return total / T_min
+
+
+def default_capacity(sse_data, T_min: float):
+    """(m_capacity, n_capacity) that the string growth rule M <- 1.5 M + 100 while n >= M/2 (src/sse.jl:138-145)
+    cannot exceed: M <= 3 n + 100 in the worst case, n <= the spectral bound (+ fluctuations)."""
+    nb = operator_count_bound(sse_data, T_min)
+    nb = nb + 8.0 * np.sqrt(nb) + 64
+    return int(3.0 * nb + 1124), int(min(nb + 256, 1 << 22))
 
 
 class MC:
@@ -28,8 +47,9 @@ class MC:
         if T.size == 1 and int(params.get("n_walkers", 1)) > 1:
             T = np.repeat(T, int(params["n_walkers"]))
         self.T = T
-        m_cap = int(params.get("m_capacity", default_capacity(self.dmodel.n_sites, self.dmodel.n_bonds, float(T.min()))))
-        n_cap = params.get("n_capacity")
+        m_def, n_def = default_capacity(self.dmodel.sse_data, float(T.min()))
+        m_cap = int(params.get("m_capacity", m_def))
+        n_cap = int(params.get("n_capacity", n_def))
         self.walkers = Walkers(
             self.dmodel,
             T,

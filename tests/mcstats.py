@@ -44,8 +44,8 @@ def run_gpu_tasks(dm, model, Ts, sweeps, therm, binsize, seed=1, m_capacity=None
 
     Ts = np.asarray(Ts, dtype=np.float64)
     Tw = np.repeat(Ts, replicas)
-    cap = m_capacity or default_capacity(dm.n_sites, dm.n_bonds, float(Ts.min()))
-    gw = Walkers(dm, Tw, m_capacity=cap, seed=seed)
+    m_def, n_def = default_capacity(dm.sse_data, float(Ts.min()))
+    gw = Walkers(dm, Tw, m_capacity=m_capacity or m_def, n_capacity=n_def if not m_capacity else None, seed=seed)
     gw.init()
     done = 0
     while done < therm:
