@@ -298,6 +298,7 @@ def run_ours(args):
             "gpu_launches": args.steps,
             "phase_cycle_share": {k: cnt[k] / max(1, cnt["cycles_diag_build"] + cnt["cycles_worm"] + cnt["cycles_commit_measure"])
                                   for k in ("cycles_diag_build", "cycles_worm", "cycles_commit_measure")},
+            "worm_cycles_per_visit": cnt["cycles_worm"] / max(1, cnt["visits"]),
             "clocks": clocks,
             "setup_s": t_setup,
         }

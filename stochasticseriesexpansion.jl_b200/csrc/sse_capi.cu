@@ -4,6 +4,7 @@
 // No CPU fallback exists: every entry point runs on the GPU or returns an error status.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -237,6 +238,26 @@ int32_t sse_model_create(const sse_model_desc *d, sse_model **out) {
         if (o < 0) { t1[i] = make_uint4(0u, 0x7ff00000u, 0u, 0u); continue; }
         t1[i] = make_uint4(outc[o].x, outc[o].y, outc[o].z, outc[o].w | ((uint32_t)(o + 1) << 6) | (uint32_t)(c - 1));
     }
+    // most likely exit leg per entrance leg, marginalised over vertices (weighted by their weight) and worms
+    uint32_t pred_exit = 0;
+    for (int leg = 0; leg < 4; ++leg) {
+        double score[4] = {0, 0, 0, 0};
+        for (int v = 0; v < nv; ++v)
+            for (int wm = 0; wm < d->max_worm; ++wm) {
+                int i = (v * d->max_worm + wm) * 4 + leg;
+                int o = d->trans_offset[i], c = d->trans_count[i];
+                if (o < 0) continue;
+                double prev = 0;
+                for (int j = 0; j < c; ++j) {
+                    score[d->out_leg[o + j]] += d->weights[v] * (d->out_cumprob[o + j] - prev);
+                    prev = d->out_cumprob[o + j];
+                }
+            }
+        int best = 0;
+        for (int j = 1; j < 4; ++j)
+            if (score[j] > score[best]) best = j;
+        pred_exit |= (uint32_t)best << (2 * leg);
+    }
     CU(upload(&m->d_bond_info, bi));
     CU(upload(&m->d_site_dim, m->site_dim));
     CU(upload(&m->d_blob, blob));
@@ -256,6 +277,8 @@ int32_t sse_model_create(const sse_model_desc *d, sse_model **out) {
     dm.site_dim = m->d_site_dim;
     dm.est_values = m->d_est;
     dm.tab_blob = m->d_blob;
+    dm.pred_exit = pred_exit;
+    dm.variant = getenv("SSE_B200_VARIANT") ? (uint32_t)atoi(getenv("SSE_B200_VARIANT")) : 0u;
     dm.tl = tl;
     *out = m;
     return 0;
@@ -288,7 +311,7 @@ int32_t sse_walkers_create(const sse_model *m, const sse_walkers_opts *o, sse_wa
     dw.n_obs = SSE_OBS_FIXED + SSE_OBS_PER_ESTIMATOR * m->dm.n_est;
     int32_t s = 0;
     s |= dev_alloc(w, &dw.ops, (size_t)W * dw.M_cap, true);
-    s |= dev_alloc(w, &dw.rec, (size_t)W * dw.n_cap, false);
+    s |= dev_alloc(w, &dw.rec, 2 * (size_t)W * dw.n_cap, false);  // 32-byte records
     s |= dev_alloc(w, &dw.state, (size_t)W * N, false);
     // per-warp state[N] + mark[N] live in shared memory when 7 CTAs/SM still fit, else in global scratch
     // level 2 (+ vlast) only while 7 CTAs/SM still fit (32 KB per CTA); level 1 up to 99 KB per CTA
@@ -631,9 +654,10 @@ int32_t sse_dbg_get_vertex_list(sse_walkers *w, int32_t i, int64_t *vertices, in
     CU(cudaMemcpy(&n, w->dw.n + i, sizeof(int), cudaMemcpyDeviceToHost));
     if (m_len < M) return fail("sse_dbg_get_vertex_list: vertices buffer too small");
     std::vector<uint32_t> ops(M), vf(N), vl(N);
-    std::vector<uint4> rec(n);
+    std::vector<uint4> rec2(2 * (size_t)n), rec(n);
     if (M) CU(cudaMemcpy(ops.data(), w->dw.ops + (size_t)i * w->dw.M_cap, sizeof(uint32_t) * M, cudaMemcpyDeviceToHost));
-    if (n) CU(cudaMemcpy(rec.data(), w->dw.rec + (size_t)i * w->dw.n_cap, sizeof(uint4) * n, cudaMemcpyDeviceToHost));
+    if (n) CU(cudaMemcpy(rec2.data(), w->dw.rec + 2 * (size_t)i * w->dw.n_cap, sizeof(uint4) * 2 * n, cudaMemcpyDeviceToHost));
+    for (int k = 0; k < n; ++k) rec[k] = rec2[2 * (size_t)k];
     CU(cudaMemcpy(vf.data(), w->dw.vfirst + (size_t)i * N, sizeof(uint32_t) * N, cudaMemcpyDeviceToHost));
     CU(cudaMemcpy(vl.data(), w->dw.vlast + (size_t)i * N, sizeof(uint32_t) * N, cudaMemcpyDeviceToHost));
     std::vector<int64_t> pos(n, -1);

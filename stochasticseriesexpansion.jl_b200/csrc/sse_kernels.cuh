@@ -8,9 +8,11 @@
 //                          (bit0 = 1, bit1 = diagonal, bits 2..13 = global vertex id, bits 14.. = bond);
 //                          "indexed" mode (between K1K2 and K4C): non-identity slots hold k+1, the index of
 //                          their vertex record, so a worm start needs ONE dependent load.
-//   rec  [W][n_cap]  16 B  vertex records {op code, 4 x 24-bit links (k' << 2 | leg')}: ONE 16-byte load per
-//                          worm visit returns the operator and all four leg links (one 32 B DRAM sector), the
-//                          visit's only store goes back into the same sector.
+//   rec  [W][n_cap]  32 B  vertex records = one DRAM sector: {op code, 4 x 24-bit links (k' << 2 | leg')} in the
+//                          first 16 bytes - ONE 16-byte load per worm visit returns the operator and all four
+//                          leg links, the visit's only store goes back into the same sector - and 4 x 24-bit
+//                          two-hop prefetch hints in the second 16 bytes (where the worm most likely is two
+//                          visits later if it leaves through that leg), used only for prefetch.global.L2.
 //   state[W][N] u8, vfirst/vlast [W][N] u32 (link of the first / last leg on each site's world line).
 //
 // Shared memory per CTA: the vertex tables (staged once) + per warp: the walker's state[N], a mark[N] byte
@@ -74,6 +76,8 @@ struct DevModel {
     const uint8_t *site_dim;  // [n_sites]
     const double *est_values; // [n_est][n_sites][est_max_dim]
     const uint8_t *tab_blob;  // TabLayout image
+    uint32_t pred_exit;       // 2 bits per entrance leg: the most likely exit leg (prefetch hints only)
+    uint32_t variant;         // tuning switches (env SSE_B200_VARIANT): 2 = no hint prefetch, 4 = no hint pass
     TabLayout tl;
 };
 
@@ -128,7 +132,7 @@ struct Ctx {
     double T, num_worms, avg_wl, last_wlf;
     int M, n;
     uint32_t flags, lane;
-    unsigned long long visits;
+    unsigned long long visits, t_wait;
 };
 
 __device__ __forceinline__ uint32_t lanemask_lt() {
@@ -175,7 +179,7 @@ __device__ __forceinline__ uint4 rec_pack(uint32_t op, uint32_t l0, uint32_t l1,
 }
 // overwrite link `leg` of record `k` (3 bytes at byte 4 + 3*leg)
 __device__ __forceinline__ void rec_patch(uint4 *rec, uint32_t target_link, uint32_t value) {
-    uint8_t *b = reinterpret_cast<uint8_t *>(rec + (target_link >> 2)) + 4 + 3 * (target_link & 3u);
+    uint8_t *b = reinterpret_cast<uint8_t *>(rec + 2u * (target_link >> 2)) + 4 + 3 * (target_link & 3u);
     b[0] = (uint8_t)value;
     b[1] = (uint8_t)(value >> 8);
     b[2] = (uint8_t)(value >> 16);
@@ -445,7 +449,8 @@ __device__ void phase_diag_build(const SmTab &st, const DevModel &dm, const DevW
                 }
                 if (sua == NONE24) c.vlast[sa] = me | 2u;  // vertex_list.jl:42
                 if (sub == NONE24) c.vlast[sb] = me | 3u;
-                c.rec[k] = rec_pack(newop, bla, blb, sua, sub);
+                c.rec[2u * k] = rec_pack(newop, bla, blb, sua, sub);
+                c.rec[2u * k + 1u] = make_uint4(0u, 0u, 0u, 0u);  // hints are filled by phase_hints
                 c.ops[p] = k + 1u;
             } else if (nonid) {
                 c.ops[p] = 0u;  // removed diagonal operator (sse.jl:179)
@@ -473,6 +478,31 @@ __device__ void phase_diag_build(const SmTab &st, const DevModel &dm, const DevW
 }
 
 // ------------------------------------------------------------------------------------------------------
+// Prefetch hints (no counterpart in the reference; affects speed only, never results).  For every record k and
+// exit leg j: the worm arrives at (k1, l1) = link_j(k); its most likely exit there is pred_exit[l1] (from the
+// vertex tables, host-computed), so two visits later it most likely needs the record link_{pred_exit[l1]}(k1).
+// Four independent random loads per lane are in flight, so this pass runs at memory-level parallelism 128.
+// ------------------------------------------------------------------------------------------------------
+__device__ void phase_hints(const DevModel &dm, Ctx &c) {
+    const uint32_t n = (uint32_t)c.n, pe = dm.pred_exit;
+    __syncwarp();
+    for (uint32_t k = c.lane; k < n; k += 32) {
+        const uint4 R = __ldcg(c.rec + 2u * k);
+        uint32_t l[4], h[4];
+        uint4 R1[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            l[j] = rec_link(R, j);
+            R1[j] = __ldcg(c.rec + 2u * (l[j] >> 2));
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) h[j] = rec_link(R1[j], (pe >> (2u * (l[j] & 3u))) & 3u);
+        c.rec[2u * k + 1u] = rec_pack(0u, h[0], h[1], h[2], h[3]);
+    }
+    __syncwarp();
+}
+
+// ------------------------------------------------------------------------------------------------------
 // worm_traverse! inner loop (src/sse.jl:262-303) with scatter (src/vertex_data.jl:106-125).
 // All 32 lanes execute the chain uniformly; the lanes pre-compute the next 64 uniform draws in parallel
 // (one Philox block each) into the warp's shared scratch.  Kept out of line with a minimal argument set so
@@ -485,7 +515,8 @@ struct WormArgs {
     const unsigned long long *inj;
     long long inj_len;
     unsigned long long seed, wid, draws;
-    uint32_t maxw, lane, k0, l0, w0, fell;
+    uint32_t maxw, lane, k0, l0, w0, fell, variant;
+    unsigned long long t_wait;
 };
 
 __device__ __forceinline__ uint4 lds128(uint32_t a) {
@@ -524,6 +555,7 @@ __device__ __forceinline__ uint4 ldg_cg128(const uint4 *p) {
     asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
     return v;
 }
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void stg_u32(void *p, uint32_t v) {
     asm volatile("st.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -531,64 +563,104 @@ __device__ __forceinline__ void stg_u32(void *p, uint32_t v) {
 // packed step (t1[].z / outc[].z): bits 1..13 = vertex bits of the op code (diag << 1 | gv << 2),
 // bits 16..17 = exit leg, bits 24..31 = exit worm;  .w: bits 24..31 = dim of the exit leg's site,
 // (t1 only) bits 6..23 = offset of the 2nd outcome, bits 0..5 = number of further outcomes.
+// loop-invariant part of a worm
+struct WormConst {
+    uint4 *rec;
+    uint32_t t1_s, outc_s, maxw4, pos0, w0;
+    bool pref;
+};
+// loop-carried part
+struct WormVar {
+    uint32_t pos, wf, len, fell;
+    uint32_t patch, patch_val;  // the previous visit re-entered its own record: its first word is patch_val
+};
+
+// One visit (the body of the reference's `while true`, src/sse.jl:274-300).  Rc/Hc = the current record (already
+// requested), Rn/Hn receive the next one.  The code is ordered so that the next record's load is ISSUED as early
+// as the data dependences allow (record -> shared-memory transition entry -> compare -> link); the store, the
+// stop tests, the prefetch and the bookkeeping execute in the shadow of that load.  Returns true when the worm closed.
+__device__ __forceinline__ bool worm_visit(const WormConst &k, WormVar &v, const uint4 &Rc, const uint4 &Hc, uint4 &Rn,
+                                           uint4 &Hn, const double r) {
+    const uint32_t pos = v.pos;
+    const uint32_t x = v.patch ? v.patch_val : Rc.x;
+    // transitions[leg_in, worm_in, vi] fused with its first outcome (vertex_data.jl:115-123)
+    uint4 e = lds128(k.t1_s + 16u * (op_gv(x) * k.maxw4 + (((v.wf - 1u) << 2) | (pos & 3u))));
+    if (!(r < __hiloint2double((int)e.y, (int)e.x))) {
+        const uint32_t off = (e.w >> 6) & 0x3ffffu, cnt = e.w & 63u;
+        bool hit = false;
+        for (uint32_t j = 0; !hit && j < cnt; ++j) {  // first out with random < cumprob
+            e = lds128(k.outc_s + 16u * (off + j));
+            hit = r < __hiloint2double((int)e.y, (int)e.x);
+        }
+        if (!hit) v.fell = 1;  // vertex_data.jl:124; clamped to the last outcome
+    }
+    const uint32_t leg_out = (e.z >> 16) & 3u;
+    const uint32_t posn = rec_link(Rc, leg_out);  // (leg_in, p) = vertices[leg_out, p] (sse.jl:295)
+    uint4 *const rn = k.rec + 2u * (posn >> 2);
+    Rn = ldg_cg128(rn);
+    Hn = ldg_cg128(rn + 1);
+    // ---- everything below overlaps with the load ----
+    const uint32_t newop = (x & ~(VMASK | 2u)) | (e.z & (VMASK | 2u));  // OperCode(bond, new_vertex) (sse.jl:285)
+    stg_u32(k.rec + 2u * (pos >> 2), newop);
+    if (k.pref) prefetch_l2(k.rec + 2u * (rec_link(Hc, leg_out) >> 2));  // two-hop hint of the leg we leave through
+    const uint32_t w_out = e.z >> 24, dim_out = e.w >> 24;
+    const bool stop1 = (((pos & ~3u) | leg_out) == k.pos0) && (w_out + k.w0 == dim_out);  // sse.jl:288-290
+    v.len += stop1 ? 0u : 1u;
+    v.wf = w_out;
+    v.patch = ((posn >> 2) == (pos >> 2)) ? 1u : 0u;  // the link re-enters this record: its load preceded the store
+    v.patch_val = newop;
+    v.pos = posn;
+    const bool stop2 = (posn == k.pos0) && (w_out == k.w0);  // sse.jl:297-299
+    return stop1 || stop2;
+}
+
 template <bool INJ>
 __device__ __noinline__ uint32_t worm_traverse_loop(WormArgs &a) {
-    uint4 *const rec = a.rec;
-    const uint32_t t1_s = a.t1_s, outc_s = a.outc_s, rbuf_s = a.rbuf_s, maxw4 = a.maxw * 4u;
-    const uint32_t pos0 = (a.k0 << 2) | a.l0, w0 = a.w0;
-    uint32_t pos = pos0, wf = w0, len = 1, fell = 0;
+    WormConst k;
+    k.rec = a.rec;
+    k.t1_s = a.t1_s;
+    k.outc_s = a.outc_s;
+    k.maxw4 = a.maxw * 4u;
+    k.pos0 = (a.k0 << 2) | a.l0;
+    k.w0 = a.w0;
+    k.pref = !(a.variant & 2u);
+    const uint32_t rbuf_s = a.rbuf_s;
+    WormVar v;
+    v.pos = k.pos0;
+    v.wf = k.w0;
+    v.len = 1;
+    v.fell = 0;
+    v.patch = 0;
+    v.patch_val = 0;
     unsigned long long j0 = a.draws >> 1;
     uint32_t ri = (uint32_t)(a.draws & 1ull);  // index into rbuf (draw 2*j0 + ri)
-    uint4 R = ldg_cg128(rec + (pos >> 2));
-    bool done = false;
+    uint4 R0 = ldg_cg128(k.rec + 2u * (v.pos >> 2)), H0 = ldg_cg128(k.rec + 2u * (v.pos >> 2) + 1u), R1, H1;
+    __syncwarp();
+    fill_u01<INJ>(a, j0);
+    __syncwarp();
     while (true) {
-        __syncwarp();
-        fill_u01<INJ>(a, j0);
-        __syncwarp();
-        while (ri < 64) {
-            const double r = lds_f64(rbuf_s + 8u * ri);  // rand(rng) (sse.jl:282)
-            ++ri;
-            // transitions[leg_in, worm_in, vi] fused with its first outcome (vertex_data.jl:115-123)
-            uint4 e = lds128(t1_s + 16u * (op_gv(R.x) * maxw4 + (((wf - 1u) << 2) | (pos & 3u))));
-            // The first outcome is by far the most likely: follow its link SPECULATIVELY so the next record's
-            // load is in flight while the compare, the store and the stop tests of this visit execute.
-            uint32_t leg_out = (e.z >> 16) & 3u;
-            uint32_t posn = rec_link(R, leg_out);  // (leg_in, p) = vertices[leg_out, p] (sse.jl:295)
-            const uint4 Rs = ldg_cg128(rec + (posn >> 2));
-            uint4 Rn;
-            if (r < __hiloint2double((int)e.y, (int)e.x)) {
-                Rn = Rs;
-            } else {
-                const uint32_t off = (e.w >> 6) & 0x3ffffu, cnt = e.w & 63u;
-                bool hit = false;
-                for (uint32_t j = 0; !hit && j < cnt; ++j) {  // first out with random < cumprob
-                    e = lds128(outc_s + 16u * (off + j));
-                    hit = r < __hiloint2double((int)e.y, (int)e.x);
-                }
-                if (!hit) fell = 1;  // vertex_data.jl:124; clamped to the last outcome
-                leg_out = (e.z >> 16) & 3u;
-                posn = rec_link(R, leg_out);
-                Rn = ldg_cg128(rec + (posn >> 2));  // issued while the mispredicted load is still in flight
-                asm volatile("" ::"r"(Rs.x), "r"(Rs.y), "r"(Rs.z), "r"(Rs.w));  // keep Rs in its own registers (no WAW wait)
-            }
-            const uint32_t w_out = e.z >> 24, dim_out = e.w >> 24;
-            const uint32_t newop = (R.x & ~(VMASK | 2u)) | (e.z & (VMASK | 2u));  // OperCode(bond, new_vertex) (sse.jl:285)
-            stg_u32(rec + (pos >> 2), newop);
-            if (((pos & ~3u) | leg_out) == pos0 && w_out + w0 == dim_out) { done = true; break; }  // sse.jl:288-290
-            ++len;
-            wf = w_out;
-            if ((posn >> 2) == (pos >> 2)) Rn.x = newop;  // the link re-enters this record: its load preceded the store
-            pos = posn;
-            R = Rn;
-            if (pos == pos0 && wf == w0) { done = true; break; }  // sse.jl:297-299
+        // two visits per iteration so the record registers ping-pong without copies
+        if (ri >= 64) {
+            j0 += 32;
+            ri = 0;
+            __syncwarp();
+            fill_u01<INJ>(a, j0);
+            __syncwarp();
         }
-        if (done) break;
-        j0 += 32;
-        ri = 0;
+        if (worm_visit(k, v, R0, H0, R1, H1, lds_f64(rbuf_s + 8u * ri++))) break;  // rand(rng) (sse.jl:282)
+        if (ri >= 64) {
+            j0 += 32;
+            ri = 0;
+            __syncwarp();
+            fill_u01<INJ>(a, j0);
+            __syncwarp();
+        }
+        if (worm_visit(k, v, R1, H1, R0, H0, lds_f64(rbuf_s + 8u * ri++))) break;
     }
     a.draws = 2ull * j0 + ri;
-    a.fell = fell;
-    return len;
+    a.fell = v.fell;
+    a.t_wait = 0;
+    return v.len;
 }
 
 template <bool INJ>
@@ -610,7 +682,10 @@ __device__ __forceinline__ uint32_t worm_traverse(const SmTab &st, const DevMode
     a.l0 = l0;
     a.w0 = w0;
     a.fell = 0;
+    a.variant = dm.variant;
+    a.t_wait = 0;
     const uint32_t len = worm_traverse_loop<INJ>(a);
+    c.t_wait += a.t_wait;
     c.draws = a.draws;
     if (a.fell) c.flags |= SSE_FLAG_SCATTER_FALLTHROUGH;
     if (INJ && (long long)c.draws > c.inj_len) c.flags |= SSE_FLAG_STREAM_EXHAUSTED;
@@ -647,7 +722,7 @@ __device__ void phase_worm_update(const SmTab &st, const DevModel &dm, const Dev
                 c.draws += 64u;
             }
         }
-        const uint4 R0 = __ldcg(c.rec + k0);
+        const uint4 R0 = __ldcg(c.rec + 2u * k0);
         const uint4 bi = __ldg(dm.bond_info + op_bond(R0.x));
         const uint32_t dim0 = (l0 & 1u) ? (bi.y >> 24) : (bi.x >> 24);  // site_of_leg (sse.jl:250)
         const uint32_t w0 = 1u + (uint32_t)sse_uint_below(draw<INJ>(c, c.draws), dim0 - 1u);  // sse.jl:251
@@ -687,7 +762,7 @@ __device__ void phase_worm_update(const SmTab &st, const DevModel &dm, const Dev
             const uint32_t d = dm.site_dim[s];
             c.state[s] = (uint8_t)(1u + (uint32_t)sse_uint_below(draw<INJ>(c, c.draws + __popc(em & lt)), d));
         } else if (act) {
-            const uint32_t op = __ldcg(reinterpret_cast<const uint32_t *>(c.rec + (f >> 2)));
+            const uint32_t op = __ldcg(reinterpret_cast<const uint32_t *>(c.rec + 2u * (f >> 2)));
             c.state[s] = (uint8_t)((st.vinfo[op_gv(op)] >> (8u * (f & 3u))) & 0xffu);
         }
         c.draws += __popc(em);
@@ -713,7 +788,7 @@ __device__ void phase_commit_measure(const SmTab &st, const DevModel &dm, const 
             const int p = ch * 32 + (int)lane;
             uint32_t op = p < M ? c.ops[p] : 0u;
             if (indexed && op != 0u) {
-                op = __ldcg(reinterpret_cast<const uint32_t *>(c.rec + (op - 1u)));
+                op = __ldcg(reinterpret_cast<const uint32_t *>(c.rec + 2u * (op - 1u)));
                 c.ops[p] = op;
             }
             if (do_measure) neg += __popc(__ballot_sync(FULL, op != 0u && st.vneg[op_gv(op)]));
@@ -838,7 +913,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 7) k_walkers(const DevMode
         c.mark = dw.mark + (size_t)w * N;
     }
     c.ops = dw.ops + (size_t)w * dw.M_cap;
-    c.rec = dw.rec + (size_t)w * dw.n_cap;
+    c.rec = dw.rec + 2 * (size_t)w * dw.n_cap;
     c.vfirst = dw.vfirst + (size_t)w * N;
     uint32_t *gvlast = dw.vlast + (size_t)w * N;
     c.vlast = dw.smem_state >= 2 ? reinterpret_cast<uint32_t *>(c.mark + ((N + 15) & ~15)) : gvlast;
@@ -855,6 +930,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 7) k_walkers(const DevMode
     c.n = dw.n[w];
     c.flags = dw.flags[w];
     c.visits = 0;
+    c.t_wait = 0;
     const uint32_t fatal = SSE_FLAG_M_OVERFLOW | SSE_FLAG_N_OVERFLOW | SSE_FLAG_STREAM_EXHAUSTED;
     if (c.flags & fatal) return;
     for (int s = c.lane; s < N; s += 32) {
@@ -871,6 +947,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 7) k_walkers(const DevMode
                 const long long t0 = clock64();
                 phase_diag_build<INJ>(st, dm, dw, c, true, true);
                 if (c.flags & fatal) break;
+                if (!(dm.variant & 4u)) phase_hints(dm, c);
                 const long long t1 = clock64();
                 phase_worm_update<INJ>(st, dm, dw, c, a.thermalized != 0, w);
                 if (c.flags & fatal) break;
@@ -938,6 +1015,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 7) k_walkers(const DevMode
         dw.n[w] = c.n;
         dw.flags[w] = c.flags;
         if (c.visits) atomicAdd(dw.counters + 0, c.visits);
+        if (c.t_wait) atomicAdd(dw.counters + 7, c.t_wait);
         if (sweeps) {
             atomicAdd(dw.counters + 1, sweeps);
             atomicAdd(dw.counters + 2, sum_n);

@@ -48,7 +48,7 @@ def test_bani2v2o8_published_results_gpu(L, skip_T_below):
     model = bani_honeycomb(L)
     dm = DeviceModel(model)
     Ts = [t["T"] for t in golden]
-    res = run_gpu_tasks(dm, model, Ts, sweeps=3000, therm=1000, binsize=100, seed=20 + L, replicas=32)
+    res = run_gpu_tasks(dm, model, Ts, sweeps=2000, therm=600, binsize=100, seed=20 + L, replicas=48)
     zs = {}
     for t, r in zip(golden, res):
         for name in ("Energy", "OperatorCount", "AbsMag", "Mag2", "Mag4", "MagChi", "BinderRatio", "SpecificHeat"):
