@@ -38,6 +38,9 @@ def lib():
         L.oracle_walker_create.argtypes = [vp, C.c_double, C.c_int32, C.c_uint64, C.c_uint64, C.c_double, C.c_double, C.c_double]
         L.oracle_walker_destroy.argtypes = [vp]
         L.oracle_set_injected_stream.argtypes = [vp, u64p, C.c_int64]
+        L.oracle_set_temperature.argtypes = [vp, C.c_double]
+        L.oracle_sweep_capped.restype = C.c_int32
+        L.oracle_sweep_capped.argtypes = [vp, C.c_int32, C.c_int32, C.c_uint64]
         L.oracle_rng_draws.restype = C.c_uint64
         L.oracle_rng_draws.argtypes = [vp]
         L.oracle_set_rng_draws.argtypes = [vp, C.c_uint64]
@@ -113,6 +116,13 @@ class OracleWalker:
         else:
             self._stream = np.ascontiguousarray(stream, dtype=np.uint64)
             self.L.oracle_set_injected_stream(self.h, self._stream.ctypes.data_as(u64p), len(self._stream))
+
+    def sweep_capped(self, n_sweeps: int, thermalized: bool, cap: int) -> bool:
+        """Screening aid: True if the walker needed more than `cap` visits (and was abandoned)."""
+        return bool(self.L.oracle_sweep_capped(self.h, n_sweeps, int(thermalized), cap))
+
+    def set_temperature(self, T: float):
+        self.L.oracle_set_temperature(self.h, float(T))
 
     @property
     def rng_draws(self) -> int:

@@ -280,6 +280,8 @@ struct MC {
     double last_wlf = NAN;
     uint64_t counters[4] = {0, 0, 0, 0};  // visits, sweeps, sum n, sum M
     uint32_t flags = 0;
+    uint64_t visit_cap = 0;            // screening aid only (tests/golden/screen_seeds.py): abandon the walker beyond this many visits
+    bool aborted = false;
     Int M() const { return Int(operators.size()) - 1; }
     Int n_obs() const { return SSE_OBS_FIXED + SSE_OBS_PER_ESTIMATOR * sse_data->n_estimators; }
 };
@@ -356,6 +358,7 @@ Int worm_traverse(MC &mc, Int l0, Int p0, Int wormfunc0) {
         leg_in = lp.first;
         p = lp.second;
         if (p == p0 && leg_in == l0 && wormfunc == wormfunc0) break;
+        if (mc.visit_cap && mc.counters[0] + uint64_t(worm_length) > mc.visit_cap) { mc.aborted = true; break; }
     }
     return worm_length;
 }
@@ -560,6 +563,14 @@ void oracle_set_injected_stream(void *w, const uint64_t *stream, int64_t len) {
     if (stream) { mc->rng.kind = 1; mc->rng.stream = stream; mc->rng.stream_len = uint64_t(len); mc->rng.pos = 0; mc->rng.exhausted = false; }
     else { mc->rng.kind = 0; }
 }
+// screening aid: returns 1 if the walker exceeded `cap` total visits (its configuration is then garbage)
+int32_t oracle_sweep_capped(void *w, int32_t n_sweeps, int32_t thermalized, uint64_t cap) {
+    MC &mc = *static_cast<MC *>(w);
+    mc.visit_cap = cap;
+    for (int i = 0; i < n_sweeps && !mc.aborted; ++i) sweep(mc, thermalized != 0, false);
+    return mc.aborted;
+}
+void oracle_set_temperature(void *w, double T) { static_cast<MC *>(w)->T = T; }  // sse.jl:403
 uint64_t oracle_rng_draws(void *w) { return static_cast<MC *>(w)->rng.pos; }
 void oracle_set_rng_draws(void *w, uint64_t pos) { static_cast<MC *>(w)->rng.pos = pos; }
 int32_t oracle_stream_exhausted(void *w) { return static_cast<MC *>(w)->rng.exhausted; }
