@@ -325,7 +325,7 @@ def main():
     ap.add_argument("--L", type=int, default=32)
     ap.add_argument("--beta", type=float, default=32.0)
     ap.add_argument("--walkers", type=int, default=4096, help="walkers per GPU")
-    ap.add_argument("--sweeps-per-step", type=int, default=16)
+    ap.add_argument("--sweeps-per-step", type=int, default=32)
     ap.add_argument("--therm", type=int, default=300)
     ap.add_argument("--deterministic", action="store_true",
                     help="energy_offset_factor=0 tables (the reference's intended but unreachable S=1/2 branch)")
