@@ -250,3 +250,74 @@ def test_overflow_is_loud():
     with pytest.raises(SSEError):
         gw.init()
         gw.sweep(50)
+
+
+def test_edge_cases_empty_and_ragged_strings():
+    """Empty strings (n = 0: worm_traverse! returns 0 without drawing, every site is redrawn), strings whose
+    length is not a multiple of the 32-slot chunk, and walkers of very different lengths in one batch."""
+    model = MODEL_CLASSES["mixed_honeycomb"]()
+    dm, om = _pair(model)
+    Ts = np.array([50.0, 50.0, 5.0, 0.5, 0.07])  # n ~ 0 at T = 50
+    W = len(Ts)
+    gw = Walkers(dm, Ts, m_capacity=8192, seed=99)
+    gw.init(init_opstring_cutoff=37, diagonal_warmup_sweeps=0)  # odd length, no warm-up: starts with n = 0
+    ows = []
+    for i in range(W):
+        ow = OracleWalker(om, float(Ts[i]), seed=99, walker_id=i)
+        ow.init(37, 0)
+        ows.append(ow)
+    for step in range(6):
+        gw.sweep(1, thermalized=step >= 3, measure=step >= 3)
+        for i, ow in enumerate(ows):
+            ow.sweep(1, thermalized=step >= 3, measure=step >= 3)
+            _same_state(gw.get_state(i), ow.get_state(), f"step {step} walker {i}")
+    n = gw.num_operators()
+    assert n[0] < 8 and n[4] > 100
+    sums, counts = gw.fetch_accumulators()
+    for i, ow in enumerate(ows):
+        osums, ocounts = ow.fetch_accumulators()
+        assert np.array_equal(counts[i], ocounts)
+        np.testing.assert_allclose(sums[i], osums, rtol=1e-12, atol=1e-300)
+
+
+def test_api_errors_are_loud():
+    from sse_b200.capi import SSEError
+
+    model = heisenberg_square(4, True)
+    dm, om = _pair(model)
+    gw = Walkers(dm, [0.5, 0.5], m_capacity=2048, seed=1)
+    gw.init()
+    gw.sweep(5)
+    st = gw.get_state(0)
+    bad = dict(st)
+    bad["num_operators"] = st["num_operators"] + 1
+    with pytest.raises(SSEError):
+        gw.set_state(0, bad)
+    bad = dict(st)
+    ops = st["operators"].copy()
+    ops[np.nonzero(ops)[0][0]] |= np.uint64(1) << np.uint64(60)  # bond index out of range
+    bad["operators"] = ops
+    with pytest.raises(SSEError):
+        gw.set_state(0, bad)
+    bad = dict(st)
+    s2 = st["state"].copy()
+    s2[0] = 3
+    bad["state"] = s2
+    with pytest.raises(SSEError):
+        gw.set_state(0, bad)
+    with pytest.raises(SSEError):
+        gw.dbg_worm_update(False)  # no vertex list built
+    with pytest.raises(SSEError):
+        gw.set_temperature([0.5, -1.0])
+    # an injected stream that runs out is reported, not silently recycled
+    gw.set_injected_stream(np.zeros((2, 16), dtype=np.uint64))
+    with pytest.raises(SSEError):
+        gw.dbg_diagonal_update()
+    with pytest.raises(SSEError):
+        Walkers(dm, [0.5], m_capacity=2048, n_capacity=1 << 23)
+
+
+def test_smoke_entry():
+    import __graft_entry__ as g
+
+    g.smoke()
