@@ -573,13 +573,12 @@ __device__ __forceinline__ void stg_u32(void *p, uint32_t v) {
 struct WormConst {
     uint4 *rec;
     uint32_t t1_s, outc_s, maxw4, pos0, w0;
-    bool pref, realload;
+    bool pref;
 };
 // loop-carried part
 struct WormVar {
     uint32_t pos, wf, len, fell;
     uint32_t patch, patch_val;  // the previous visit re-entered its own record: its first word is patch_val
-    uint32_t junk, touch;        // experiment (variant 8): a real load instead of the L2 prefetch hint
 };
 
 // One visit (the body of the reference's `while true`, src/sse.jl:274-300).  Rc/Hc = the current record (already
@@ -609,15 +608,9 @@ __device__ __forceinline__ bool worm_visit(const WormConst &k, WormVar &v, const
     // ---- everything below overlaps with the load ----
     const uint32_t newop = (x & ~(VMASK | 2u)) | (e.z & (VMASK | 2u));  // OperCode(bond, new_vertex) (sse.jl:285)
     stg_u32(k.rec + 2u * (pos >> 2), newop);
-    if (k.pref) {  // two-hop hint of the leg we leave through
-        const uint4 *hp = k.rec + 2u * (rec_link(Hc, leg_out) >> 2);
-        if (k.realload) {
-            v.junk ^= v.touch;  // consume the previous visit's touch load (one visit later)
-            asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(v.touch) : "l"(hp));
-        } else {
-            prefetch_l2(hp);
-        }
-    }
+    // two-hop hint of the leg we leave through.  (Tried and rejected on B200, see DESIGN.md: a real touch load
+    // instead of the hint, three-hop hints, speculating on the first outcome, parking the stores in registers.)
+    if (k.pref) prefetch_l2(k.rec + 2u * (rec_link(Hc, leg_out) >> 2));
     const uint32_t w_out = e.z >> 24, dim_out = e.w >> 24;
     const bool stop1 = (((pos & ~3u) | leg_out) == k.pos0) && (w_out + k.w0 == dim_out);  // sse.jl:288-290
     v.len += stop1 ? 0u : 1u;
@@ -639,7 +632,6 @@ __device__ __noinline__ uint32_t worm_traverse_loop(WormArgs &a) {
     k.pos0 = (a.k0 << 2) | a.l0;
     k.w0 = a.w0;
     k.pref = !(a.variant & 2u);
-    k.realload = (a.variant & 8u) != 0;
     const uint32_t rbuf_s = a.rbuf_s;
     WormVar v;
     v.pos = k.pos0;
@@ -648,8 +640,6 @@ __device__ __noinline__ uint32_t worm_traverse_loop(WormArgs &a) {
     v.fell = 0;
     v.patch = 0;
     v.patch_val = 0;
-    v.junk = 0;
-    v.touch = 0;
     unsigned long long j0 = a.draws >> 1;
     uint32_t ri = (uint32_t)(a.draws & 1ull);  // index into rbuf (draw 2*j0 + ri)
     uint4 R0 = ldg_cg128(k.rec + 2u * (v.pos >> 2)), H0 = ldg_cg128(k.rec + 2u * (v.pos >> 2) + 1u), R1, H1;
@@ -676,8 +666,8 @@ __device__ __noinline__ uint32_t worm_traverse_loop(WormArgs &a) {
         if (worm_visit(k, v, R1, H1, R0, H0, lds_f64(rbuf_s + 8u * ri++))) break;
     }
     a.draws = 2ull * j0 + ri;
-    a.fell = v.fell | ((v.junk ^ v.touch) == 0x12345u ? 1u : 0u) * 0u;
-    a.t_wait = (v.junk ^ v.touch) & 0u;
+    a.fell = v.fell;
+    a.t_wait = 0;
     return v.len;
 }
 
