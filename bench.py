@@ -124,6 +124,17 @@ class ClockSampler:
                 "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def measured_traffic_per_walker_sweep():
+    """DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) per walker-sweep from the committed ncu --set full
+    capture of this kernel on this workload (profiles/r1_d_dram_traffic.json); None if absent."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_d_dram_traffic.json")) as f:
+            d = json.load(f)
+        return float(d["dram_bytes_per_walker_sweep"]), d["source"]
+    except Exception:
+        return None, None
+
+
 def algorithmic_bytes(sum_M, sum_n, visits, measured_sweeps=0):
     """B_sweep = 8M (K1 read+write op codes) + 4M + 16n (K2) + 64V (K3) (+4M per measured sweep)."""
     return 8.0 * sum_M + 4.0 * sum_M + 16.0 * sum_n + 64.0 * visits + 4.0 * measured_sweeps
@@ -275,6 +286,9 @@ def run_ours(args):
         b_launch = algorithmic_bytes(cnt["sum_M"], cnt["sum_n"], cnt["visits"]) / args.steps
         avg_launch_ms = float(np.mean(launch_ms))
         achieved = b_launch / (avg_launch_ms * 1e-3) / 1e9
+        tpws, tsrc = measured_traffic_per_walker_sweep()
+        default_workload = (args.L == 32 and args.beta == 32.0 and not args.deterministic)
+        traffic = tpws * cnt["sweeps"] / args.steps if (tpws and default_workload) else None
         line = {
             "metric": METRIC, "value": visits / (ms_total * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -288,7 +302,7 @@ def run_ours(args):
             },
             "sweeps_per_s": sweeps / (ms_total * 1e-3),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "kernel": "sse::k_walkers<false>",
+                         "traffic": traffic, "traffic_source": tsrc if traffic else None, "peak_source": peak_src, "kernel": "sse::k_walkers<false>",
                          "avg_launch_ms": avg_launch_ms, "algorithmic_bytes_per_launch": b_launch,
                          "formula": "12*M + 16*n + 64*V per walker-sweep (SURVEY.md 8d)"},
             "e2e": {"value": visits2 / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 8 * W,
