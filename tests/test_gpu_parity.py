@@ -321,3 +321,45 @@ def test_smoke_entry():
     import __graft_entry__ as g
 
     g.smoke()
+
+
+def test_mc_carlo_interface_and_checkpoint():
+    """The Carlo-facing mirror (mc.MC + carlo.run): Carlo's sweep!/measure! loop and the device-resident loop are
+    the same Markov chain with the same per-bin sums; write_checkpoint/read_checkpoint resume it exactly."""
+    import sse_b200 as S
+    from sse_b200.carlo import MCContext, run
+    from sse_b200.mc import MC, evaluate_group
+
+    params = dict(model=S.MagnetModel, lattice=dict(unitcell=S.UnitCells.chain, size=(16,)), J=1.0, T=0.1,
+                  n_walkers=8, measure=["magnetization", "staggered_magnetization"], seed=5, sweeps=40,
+                  thermalization=30, binsize=10)  # BASELINE config 0: spin-1/2 chain L=16, T=0.1
+    mc_a, mc_b = MC(params), MC(params)
+    ctx_b = run(mc_b, params, fused=True)
+    # Carlo's own loop: sweep!; sweeps += 1; measure! once thermalised (one launch per call)
+    ctx_a = MCContext(params)
+    mc_a.init(ctx_a, params)
+    for s in range(params["thermalization"]):
+        mc_a.sweep_many(ctx_a, 1, thermalized=False, measure=False)
+    for s in range(params["sweeps"]):
+        mc_a.sweep_many(ctx_a, 1, thermalized=True, measure=False)
+        mc_a.measure(ctx_a)
+    for name in ("Sign", "OperatorCount", "SignEnergy", "SignMag2", "SignStagMag2", "SignStagMagChi"):
+        a, b = ctx_a.bin_array(name), ctx_b.bin_array(name)
+        assert a.shape == b.shape == (4, 8)
+        np.testing.assert_allclose(a, b, rtol=1e-12, atol=1e-300)
+    res = evaluate_group(ctx_b, mc_b, range(8))
+    assert -0.47 < res["Energy"][0] < -0.42  # e0(L=16 chain) ~ -0.446 per site
+    assert set(res) >= {"Energy", "SpecificHeat", "Mag", "StagMag2", "StagBinderRatio", "StagMagChi"}
+    # checkpoint round trip through the reference's five fields
+    ck = mc_b.write_checkpoint()
+    mc_c = MC(params)
+    mc_c.read_checkpoint(ck)
+    ctx_c = MCContext(params)
+    mc_b.sweep_many(ctx_b, 7, thermalized=True, measure=False)
+    mc_c.sweep_many(ctx_c, 7, thermalized=True, measure=False)
+    for i in (0, 7):
+        _same_state(mc_b.walkers.get_state(i), mc_c.walkers.get_state(i), f"checkpoint walker {i}")
+    lw = mc_b.parallel_tempering_log_weight_ratio("T", 0.2)
+    assert lw.shape == (8,) and np.all(lw < 0)
+    with pytest.raises(ValueError):
+        mc_b.parallel_tempering_change_parameter("J", 1.0)
