@@ -4,6 +4,7 @@
 // No CPU fallback exists: every entry point runs on the GPU or returns an error status.
 #include <cmath>
 #include <cstdio>
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 #include <string>
@@ -318,6 +319,7 @@ int32_t sse_walkers_create(const sse_model *m, const sse_walkers_opts *o, sse_wa
     dw.smem_state = 0;
     if (m->dm.tl.bytes + WARPS_PER_CTA * warp_scratch_bytes(N, 1) <= 99 * 1024) dw.smem_state = 1;
     if (m->dm.tl.bytes + WARPS_PER_CTA * warp_scratch_bytes(N, 2) <= 32 * 1024) dw.smem_state = 2;
+    if (const char *lv = getenv("SSE_B200_SMEM_LEVEL")) dw.smem_state = std::min(dw.smem_state, std::max(0, atoi(lv)));  // tests: force the large-lattice paths
     if (!dw.smem_state) s |= dev_alloc(w, &dw.mark, (size_t)W * N, true);
     s |= dev_alloc(w, &dw.vfirst, (size_t)W * N, false);
     s |= dev_alloc(w, &dw.vlast, (size_t)W * N, false);

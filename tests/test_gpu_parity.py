@@ -363,3 +363,33 @@ def test_mc_carlo_interface_and_checkpoint():
     assert lw.shape == (8,) and np.all(lw < 0)
     with pytest.raises(ValueError):
         mc_b.parallel_tempering_change_parameter("J", 1.0)
+
+
+@pytest.mark.parametrize("level", [0, 1])
+def test_large_lattice_memory_paths(level, monkeypatch):
+    """Lattices too large for the per-warp shared-memory arrays keep vlast (level 1) or state/mark/vlast (level 0)
+    in global memory.  Force those paths on a small model and require the same bit-exact trajectory."""
+    monkeypatch.setenv("SSE_B200_SMEM_LEVEL", str(level))
+    model = MODEL_CLASSES["spin1_dz"]()
+    dm, om = _pair(model)
+    Ts = np.array([0.2, 0.6, 1.5])
+    gw = Walkers(dm, Ts, m_capacity=8192, seed=77)
+    gw.init()
+    gw.sweep(30, thermalized=False)
+    gw.sweep(10, thermalized=True, measure=True)
+    sums, counts = gw.fetch_accumulators()
+    for i in range(len(Ts)):
+        ow = OracleWalker(om, float(Ts[i]), seed=77, walker_id=i)
+        ow.init()
+        ow.sweep(30, thermalized=False)
+        ow.sweep(10, thermalized=True, measure=True)
+        _same_state(gw.get_state(i), ow.get_state(), f"level {level} walker {i}")
+        osums, ocounts = ow.fetch_accumulators()
+        np.testing.assert_allclose(sums[i], osums, rtol=1e-12, atol=1e-300)
+    # the vertex list read-back works without the shared-memory vlast copy as well
+    gw.dbg_make_vertex_list()
+    ow.make_vertex_list()
+    M = len(ow.get_state()["operators"])
+    gv, gf, gl = gw.dbg_get_vertex_list(len(Ts) - 1, M)
+    ov, of, ol = ow.get_vertex_list()
+    assert np.array_equal(gv, ov) and np.array_equal(gf, of) and np.array_equal(gl, ol)
