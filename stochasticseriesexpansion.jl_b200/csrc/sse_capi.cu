@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -127,6 +128,8 @@ int32_t ensure_committed(sse_walkers *w) {
 
 extern "C" {
 
+int32_t sse_model_destroy(sse_model *m);
+
 const char *sse_last_error(void) { return g_err.c_str(); }
 int32_t sse_abi_version(void) { return SSE_B200_ABI_VERSION; }
 
@@ -138,7 +141,8 @@ int32_t sse_model_create(const sse_model_desc *d, sse_model **out) {
     if (d->n_bonds >= (1 << (32 - BOND_SHIFT))) return fail("sse_model_create: more than 262143 bonds is not supported");
     if (d->n_sites >= (1 << 24)) return fail("sse_model_create: more than 2^24 sites is not supported");
     if (d->max_worm < 1 || d->max_worm > 254) return fail("sse_model_create: max_worm out of range");
-    auto m = new sse_model();
+    std::unique_ptr<sse_model, int32_t (*)(sse_model *)> guard(new sse_model(), sse_model_destroy);  // freed on every error path
+    sse_model *m = guard.get();
     CU(cudaGetDevice(&m->device));
     m->n_types = d->n_types;
     m->bond_type.assign(d->bond_type, d->bond_type + d->n_bonds);
@@ -160,13 +164,11 @@ int32_t sse_model_create(const sse_model_desc *d, sse_model **out) {
         int t = d->bond_type[b];
         int sa = d->bond_sites[2 * b], sb = d->bond_sites[2 * b + 1];
         if (t < 0 || t >= d->n_types || sa < 0 || sb < 0 || sa >= d->n_sites || sb >= d->n_sites) {
-            delete m;
             return fail("sse_model_create: bond " + std::to_string(b) + " out of range");
         }
-        if (sa == sb) { delete m; return fail("sse_model_create: bonds connecting a site to itself are not supported"); }
+        if (sa == sb) { return fail("sse_model_create: bonds connecting a site to itself are not supported"); }
         int da = d->type_dims[2 * t], db = d->type_dims[2 * t + 1];
         if (da != d->site_dim[sa] || db != d->site_dim[sb]) {
-            delete m;
             return fail("SSEData: site dimensions set by VertexData are inconsistent (bond " + std::to_string(b) + ")");
         }
         bi[b] = make_uint4((uint32_t)sa | ((uint32_t)da << 24), (uint32_t)sb | ((uint32_t)db << 24),
@@ -185,7 +187,7 @@ int32_t sse_model_create(const sse_model_desc *d, sse_model **out) {
     tl.off_diagv = take(2 * n_diag);
     tl.off_vneg = take(nv);
     tl.bytes = off;
-    if (tl.bytes > 64 * 1024) { delete m; return fail("sse_model_create: vertex tables exceed the 64 KB shared-memory budget"); }
+    if (tl.bytes > 64 * 1024) { return fail("sse_model_create: vertex tables exceed the 64 KB shared-memory budget"); }
     std::vector<uint8_t> blob(tl.bytes, 0);
     auto *outc = reinterpret_cast<uint4 *>(blob.data() + tl.off_outc);
     auto *wts = reinterpret_cast<double *>(blob.data() + tl.off_weights);
@@ -209,7 +211,7 @@ int32_t sse_model_create(const sse_model_desc *d, sse_model **out) {
     for (int i = 0; i < n_trans; ++i) {
         int o = d->trans_offset[i], c = d->trans_count[i];
         if (o < 0) continue;
-        if (c < 1 || c > 64 || o + c > n_out || o + 1 >= (1 << 18)) { delete m; return fail("sse_model_create: bad transition entry (at most 64 outcomes per transition, 2^18 outcomes in total)"); }
+        if (c < 1 || c > 64 || o + c > n_out || o + 1 >= (1 << 18)) { return fail("sse_model_create: bad transition entry (at most 64 outcomes per transition, 2^18 outcomes in total)"); }
         int v = i / (d->max_worm * 4);
         for (int j = 0; j < c; ++j) otype[o + j] = vtype[v];
     }
@@ -221,7 +223,6 @@ int32_t sse_model_create(const sse_model_desc *d, sse_model **out) {
             int leg = d->out_leg[o], worm = d->out_worm[o];
             int gv = d->type_vertex_off[t] + tv - 1;
             if (tv < 1 || gv >= d->type_vertex_off[t + 1] || leg < 0 || leg > 3 || worm < 1 || worm > 254) {
-                delete m;
                 return fail("sse_model_create: bad outcome entry");
             }
             int dim_out = d->type_dims[2 * t + (leg & 1)];
@@ -281,7 +282,7 @@ int32_t sse_model_create(const sse_model_desc *d, sse_model **out) {
     dm.pred_exit = pred_exit;
     dm.variant = getenv("SSE_B200_VARIANT") ? (uint32_t)atoi(getenv("SSE_B200_VARIANT")) : 0u;
     dm.tl = tl;
-    *out = m;
+    *out = guard.release();
     return 0;
 }
 
