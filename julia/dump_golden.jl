@@ -68,7 +68,7 @@ function dump_case(name, params, outdir; sweeps = 6, ndraws = 400_000, seed = 1)
         after_diag = Dict("operators" => [op.code for op in mc.operators], "state" => Int.(mc.state),
             "num_operators" => mc.num_operators, "draws" => ctx.rng.pos)
         S.make_vertex_list!(mc.vertex_list, mc.operators, mc.sse_data.bonds)
-        vl = Dict("vertices" => [collect(t) for t in vec(permutedims(mc.vertex_list.vertices))],
+        vl = Dict("vertices" => [collect(t) for t in vec(mc.vertex_list.vertices)],
             "v_first" => [collect(t) for t in mc.vertex_list.v_first],
             "v_last" => [collect(t) for t in mc.vertex_list.v_last])
         S.worm_update(mc, ctx)
