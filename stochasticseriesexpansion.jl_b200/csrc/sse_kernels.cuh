@@ -132,7 +132,7 @@ struct Ctx {
     double T, num_worms, avg_wl, last_wlf;
     int M, n;
     uint32_t flags, lane;
-    unsigned long long visits, t_wait;
+    unsigned long long visits;
 };
 
 __device__ __forceinline__ uint32_t lanemask_lt() {
@@ -522,7 +522,6 @@ struct WormArgs {
     long long inj_len;
     unsigned long long seed, wid, draws;
     uint32_t maxw, lane, k0, l0, w0, fell, variant;
-    unsigned long long t_wait;
 };
 
 __device__ __forceinline__ uint4 lds128(uint32_t a) {
@@ -667,7 +666,6 @@ __device__ __noinline__ uint32_t worm_traverse_loop(WormArgs &a) {
     }
     a.draws = 2ull * j0 + ri;
     a.fell = v.fell;
-    a.t_wait = 0;
     return v.len;
 }
 
@@ -691,9 +689,7 @@ __device__ __forceinline__ uint32_t worm_traverse(const SmTab &st, const DevMode
     a.w0 = w0;
     a.fell = 0;
     a.variant = dm.variant;
-    a.t_wait = 0;
     const uint32_t len = worm_traverse_loop<INJ>(a);
-    c.t_wait += a.t_wait;
     c.draws = a.draws;
     if (a.fell) c.flags |= SSE_FLAG_SCATTER_FALLTHROUGH;
     if (INJ && (long long)c.draws > c.inj_len) c.flags |= SSE_FLAG_STREAM_EXHAUSTED;
@@ -938,7 +934,6 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 7) k_walkers(const DevMode
     c.n = dw.n[w];
     c.flags = dw.flags[w];
     c.visits = 0;
-    c.t_wait = 0;
     const uint32_t fatal = SSE_FLAG_M_OVERFLOW | SSE_FLAG_N_OVERFLOW | SSE_FLAG_STREAM_EXHAUSTED;
     if (c.flags & fatal) return;
     for (int s = c.lane; s < N; s += 32) {
@@ -1023,7 +1018,6 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 7) k_walkers(const DevMode
         dw.n[w] = c.n;
         dw.flags[w] = c.flags;
         if (c.visits) atomicAdd(dw.counters + 0, c.visits);
-        if (c.t_wait) atomicAdd(dw.counters + 7, c.t_wait);
         if (sweeps) {
             atomicAdd(dw.counters + 1, sweeps);
             atomicAdd(dw.counters + 2, sum_n);

@@ -125,8 +125,7 @@ class Walkers:
         out = np.zeros(8, dtype=np.uint64)
         check(self.L.sse_fetch_counters(self.handle, out.ctypes.data_as(u64p), int(reset)))
         return dict(visits=int(out[0]), sweeps=int(out[1]), sum_n=int(out[2]), sum_M=int(out[3]),
-                    cycles_diag_build=int(out[4]), cycles_worm=int(out[5]), cycles_commit_measure=int(out[6]),
-                    cycles_record_stall=int(out[7]))
+                    cycles_diag_build=int(out[4]), cycles_worm=int(out[5]), cycles_commit_measure=int(out[6]))
 
     def get_state(self, walker: int) -> dict:
         ops = np.zeros(self.m_capacity + 32, dtype=np.uint64)
