@@ -393,3 +393,30 @@ def test_large_lattice_memory_paths(level, monkeypatch):
     gv, gf, gl = gw.dbg_get_vertex_list(len(Ts) - 1, M)
     ov, of, ol = ow.get_vertex_list()
     assert np.array_equal(gv, ov) and np.array_equal(gf, of) and np.array_equal(gl, ol)
+
+
+def test_replica_exchange_on_device_walkers():
+    """Parallel-tempering hooks (sse.jl:390-405) driven by tempering.ReplicaExchange: temperatures stay a permutation
+    of the ladder, the device sees the new temperatures, swaps do happen, and configurations stay consistent."""
+    from sse_b200.tempering import ReplicaExchange
+
+    model = heisenberg_square(4, False)
+    dm, om = _pair(model)
+    ladder = np.linspace(0.3, 1.2, 12)
+    gw = Walkers(dm, ladder, m_capacity=4096, seed=8)
+    gw.init()
+    gw.sweep(50, thermalized=False)
+    rx = ReplicaExchange(gw, seed=1)
+    for _ in range(20):
+        gw.sweep(3, thermalized=True)
+        T_new = rx.step()
+        assert np.allclose(np.sort(T_new), ladder)
+    assert rx.proposed > 0 and 0 < rx.accepted <= rx.proposed
+    for i in (0, 5, 11):
+        st = gw.get_state(i)
+        assert st["T"] == gw.T[i]
+        assert isconsistent(st["operators"], st["state"], om.sse_data)
+    # colder temperature labels end up on longer operator strings on average
+    n = gw.num_operators()
+    order = np.argsort(gw.T)
+    assert n[order[:3]].mean() > n[order[-3:]].mean()
