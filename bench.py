@@ -333,14 +333,15 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=4)
+    ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--L", type=int, default=32)
     ap.add_argument("--beta", type=float, default=32.0)
     ap.add_argument("--walkers", type=int, default=4096, help="walkers per GPU")
-    ap.add_argument("--sweeps-per-step", type=int, default=100,
-                    help="sweeps per launch (= one Carlo bin; the reference tutorial uses binsize 100)")
+    ap.add_argument("--sweeps-per-step", type=int, default=64,
+                    help="sweeps per launch (one Carlo bin; the reference tutorial uses binsize 100). Longer launches "
+                         "average the per-walker worm-length imbalance: busy fraction 81 %% at 32, 86 %% at 100")
     ap.add_argument("--therm", type=int, default=300)
     ap.add_argument("--deterministic", action="store_true",
                     help="energy_offset_factor=0 tables (the reference's intended but unreachable S=1/2 branch)")
