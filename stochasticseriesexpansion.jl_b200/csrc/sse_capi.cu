@@ -669,10 +669,7 @@ int32_t sse_dbg_get_vertex_list(sse_walkers *w, int32_t i, int64_t *vertices, in
             if (ops[p] - 1 >= (uint32_t)n) return fail("sse_dbg_get_vertex_list: corrupt record index");
             pos[ops[p] - 1] = p;
         }
-    auto link = [&](const uint4 &r, int j) -> uint32_t {
-        unsigned __int128 v = (unsigned __int128)r.y | ((unsigned __int128)r.z << 32) | ((unsigned __int128)r.w << 64);
-        return (uint32_t)((v >> (24 * j)) & 0xffffffu);
-    };
+    auto link = [&](const uint4 &r, int j) -> uint32_t { return j == 0 ? r.x : j == 1 ? r.y : j == 2 ? r.z : r.w; };
     for (int64_t p = 0; p < M; ++p)
         for (int l = 0; l < 4; ++l) {
             int64_t *dst = vertices + (p * 4 + l) * 2;

@@ -8,11 +8,11 @@
 //                          (bit0 = 1, bit1 = diagonal, bits 2..13 = global vertex id, bits 14.. = bond);
 //                          "indexed" mode (between K1K2 and K4C): non-identity slots hold k+1, the index of
 //                          their vertex record, so a worm start needs ONE dependent load.
-//   rec  [W][n_cap]  32 B  vertex records = one DRAM sector: {op code, 4 x 24-bit links (k' << 2 | leg')} in the
-//                          first 16 bytes - ONE 16-byte load per worm visit returns the operator and all four
-//                          leg links, the visit's only store goes back into the same sector - and 4 x 24-bit
-//                          two-hop prefetch hints in the second 16 bytes (where the worm most likely is two
-//                          visits later if it leaves through that leg), used only for prefetch.global.L2.
+//   rec  [W][n_cap]  32 B  vertex records = one DRAM sector.  First 16 bytes: the four leg links as u32
+//                          (k' << 2 | leg').  Second 16 bytes: the op code + 4 x 24-bit two-hop prefetch hints
+//                          (where the worm most likely is two visits later if it leaves through that leg; used
+//                          only for prefetch.global.L2).  Both halves arrive with one sector per worm visit,
+//                          the visit's only store (the op code) goes back into the same sector.
 //   state[W][N] u8, vfirst/vlast [W][N] u32 (link of the first / last leg on each site's world line).
 //
 // Shared memory per CTA: the vertex tables (staged once) + per warp: the walker's state[N], a mark[N] byte
@@ -163,7 +163,12 @@ __device__ __forceinline__ uint64_t scratch_draw(const Ctx &c, unsigned long lon
     return c.rng[k - 2ull * j0];
 }
 
-// link j (24 bits) of a record: bits [24j, 24j+24) of the 96-bit little-endian field (y, z, w)
+// leg link j of a record's first half (plain u32 words)
+__device__ __forceinline__ uint32_t rec_sel(const uint4 &r, uint32_t j) {
+    const uint32_t a = (j & 1u) ? r.y : r.x, b = (j & 1u) ? r.w : r.z;
+    return (j & 2u) ? b : a;
+}
+// hint j (24 bits) of a record's second half: bits [24j, 24j+24) of the 96-bit little-endian field (y, z, w)
 __device__ __forceinline__ uint32_t rec_link(const uint4 &r, uint32_t j) {
     uint32_t lo = (j < 2) ? r.y : ((j == 2) ? r.z : r.w);
     uint32_t hi = (j < 2) ? r.z : r.w;
@@ -177,12 +182,9 @@ __device__ __forceinline__ uint4 rec_pack(uint32_t op, uint32_t l0, uint32_t l1,
     r.w = (l2 >> 16) | (l3 << 8);
     return r;
 }
-// overwrite link `leg` of record `k` (3 bytes at byte 4 + 3*leg)
+// overwrite link `leg` of record `k` (one aligned word)
 __device__ __forceinline__ void rec_patch(uint4 *rec, uint32_t target_link, uint32_t value) {
-    uint8_t *b = reinterpret_cast<uint8_t *>(rec + 2u * (target_link >> 2)) + 4 + 3 * (target_link & 3u);
-    b[0] = (uint8_t)value;
-    b[1] = (uint8_t)(value >> 8);
-    b[2] = (uint8_t)(value >> 16);
+    reinterpret_cast<uint32_t *>(rec + 2u * (target_link >> 2))[target_link & 3u] = value;
 }
 
 __device__ __forceinline__ double shfl_f64(double v, int src) {
@@ -449,8 +451,8 @@ __device__ void phase_diag_build(const SmTab &st, const DevModel &dm, const DevW
                 }
                 if (sua == NONE24) c.vlast[sa] = me | 2u;  // vertex_list.jl:42
                 if (sub == NONE24) c.vlast[sb] = me | 3u;
-                c.rec[2u * k] = rec_pack(newop, bla, blb, sua, sub);
-                c.rec[2u * k + 1u] = make_uint4(0u, 0u, 0u, 0u);  // hints are filled by phase_hints
+                c.rec[2u * k] = make_uint4(bla, blb, sua, sub);          // links still unknown stay NONE24 until patched
+                c.rec[2u * k + 1u] = make_uint4(newop, 0u, 0u, 0u);      // hints are filled by phase_hints
                 c.ops[p] = k + 1u;
             } else if (nonid) {
                 c.ops[p] = 0u;  // removed diagonal operator (sse.jl:179)
@@ -488,22 +490,18 @@ __device__ void phase_hints(const DevModel &dm, Ctx &c) {
     __syncwarp();
     for (uint32_t k = c.lane; k < n; k += 32) {
         const uint4 R = __ldcg(c.rec + 2u * k);
-        uint32_t l[4], h[4];
+        const uint32_t l[4] = {R.x, R.y, R.z, R.w};
+        uint32_t h[4];
         uint4 R1[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            l[j] = rec_link(R, j);
-            R1[j] = __ldcg(c.rec + 2u * (l[j] >> 2));
-        }
+        for (int j = 0; j < 4; ++j) R1[j] = __ldcg(c.rec + 2u * (l[j] >> 2));
 #pragma unroll
-        for (int j = 0; j < 4; ++j) h[j] = rec_link(R1[j], (pe >> (2u * (l[j] & 3u))) & 3u);
-        if (dm.variant & 16u) {  // three-hop hints: one more predicted step (prefetch lead of two visits)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) R1[j] = __ldcg(c.rec + 2u * (h[j] >> 2));
-#pragma unroll
-            for (int j = 0; j < 4; ++j) h[j] = rec_link(R1[j], (pe >> (2u * (h[j] & 3u))) & 3u);
-        }
-        c.rec[2u * k + 1u] = rec_pack(0u, h[0], h[1], h[2], h[3]);
+        for (int j = 0; j < 4; ++j) h[j] = rec_sel(R1[j], (pe >> (2u * (l[j] & 3u))) & 3u);
+        const uint4 H = rec_pack(0u, h[0], h[1], h[2], h[3]);
+        uint32_t *dst = reinterpret_cast<uint32_t *>(c.rec + 2u * k + 1u);  // word 0 is the op code: keep it
+        dst[1] = H.y;
+        dst[2] = H.z;
+        dst[3] = H.w;
     }
     __syncwarp();
 }
@@ -587,7 +585,7 @@ struct WormVar {
 __device__ __forceinline__ bool worm_visit(const WormConst &k, WormVar &v, const uint4 &Rc, const uint4 &Hc, uint4 &Rn,
                                            uint4 &Hn, const double r) {
     const uint32_t pos = v.pos;
-    const uint32_t x = v.patch ? v.patch_val : Rc.x;
+    const uint32_t x = v.patch ? v.patch_val : Hc.x;  // Rc = the four links, Hc = {op code, hints}
     // transitions[leg_in, worm_in, vi] fused with its first outcome (vertex_data.jl:115-123)
     uint4 e = lds128(k.t1_s + 16u * (op_gv(x) * k.maxw4 + (((v.wf - 1u) << 2) | (pos & 3u))));
     if (!(r < __hiloint2double((int)e.y, (int)e.x))) {
@@ -600,13 +598,13 @@ __device__ __forceinline__ bool worm_visit(const WormConst &k, WormVar &v, const
         if (!hit) v.fell = 1;  // vertex_data.jl:124; clamped to the last outcome
     }
     const uint32_t leg_out = (e.z >> 16) & 3u;
-    const uint32_t posn = rec_link(Rc, leg_out);  // (leg_in, p) = vertices[leg_out, p] (sse.jl:295)
+    const uint32_t posn = rec_sel(Rc, leg_out);  // (leg_in, p) = vertices[leg_out, p] (sse.jl:295)
     uint4 *const rn = k.rec + 2u * (posn >> 2);
     Rn = ldg_cg128(rn);
     Hn = ldg_cg128(rn + 1);
     // ---- everything below overlaps with the load ----
     const uint32_t newop = (x & ~(VMASK | 2u)) | (e.z & (VMASK | 2u));  // OperCode(bond, new_vertex) (sse.jl:285)
-    stg_u32(k.rec + 2u * (pos >> 2), newop);
+    stg_u32(k.rec + 2u * (pos >> 2) + 1u, newop);
     // two-hop hint of the leg we leave through.  (Tried and rejected on B200, see DESIGN.md: a real touch load
     // instead of the hint, three-hop hints, speculating on the first outcome, parking the stores in registers.)
     if (k.pref) prefetch_l2(k.rec + 2u * (rec_link(Hc, leg_out) >> 2));
@@ -726,7 +724,7 @@ __device__ void phase_worm_update(const SmTab &st, const DevModel &dm, const Dev
                 c.draws += 64u;
             }
         }
-        const uint4 R0 = __ldcg(c.rec + 2u * k0);
+        const uint4 R0 = __ldcg(c.rec + 2u * k0 + 1u);  // {op code, hints}
         const uint4 bi = __ldg(dm.bond_info + op_bond(R0.x));
         const uint32_t dim0 = (l0 & 1u) ? (bi.y >> 24) : (bi.x >> 24);  // site_of_leg (sse.jl:250)
         const uint32_t w0 = 1u + (uint32_t)sse_uint_below(draw<INJ>(c, c.draws), dim0 - 1u);  // sse.jl:251
@@ -766,7 +764,7 @@ __device__ void phase_worm_update(const SmTab &st, const DevModel &dm, const Dev
             const uint32_t d = dm.site_dim[s];
             c.state[s] = (uint8_t)(1u + (uint32_t)sse_uint_below(draw<INJ>(c, c.draws + __popc(em & lt)), d));
         } else if (act) {
-            const uint32_t op = __ldcg(reinterpret_cast<const uint32_t *>(c.rec + 2u * (f >> 2)));
+            const uint32_t op = __ldcg(reinterpret_cast<const uint32_t *>(c.rec + 2u * (f >> 2) + 1u));
             c.state[s] = (uint8_t)((st.vinfo[op_gv(op)] >> (8u * (f & 3u))) & 0xffu);
         }
         c.draws += __popc(em);
@@ -792,7 +790,7 @@ __device__ void phase_commit_measure(const SmTab &st, const DevModel &dm, const 
             const int p = ch * 32 + (int)lane;
             uint32_t op = p < M ? c.ops[p] : 0u;
             if (indexed && op != 0u) {
-                op = __ldcg(reinterpret_cast<const uint32_t *>(c.rec + 2u * (op - 1u)));
+                op = __ldcg(reinterpret_cast<const uint32_t *>(c.rec + 2u * (op - 1u) + 1u));
                 c.ops[p] = op;
             }
             if (do_measure) neg += __popc(__ballot_sync(FULL, op != 0u && st.vneg[op_gv(op)]));
