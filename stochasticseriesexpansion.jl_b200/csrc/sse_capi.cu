@@ -15,6 +15,11 @@
 
 using namespace sse;
 
+// Kernel launches go through one macro so that the test-only warp emulator (tests/emu) can compile this file with g++.
+#ifndef SSE_LAUNCH_KERNEL
+#define SSE_LAUNCH_KERNEL(kern, grid, block, smem_bytes, stream, ...) kern<<<grid, block, smem_bytes, stream>>>(__VA_ARGS__)
+#endif
+
 namespace {
 
 thread_local std::string g_err;
@@ -97,9 +102,9 @@ int32_t launch(sse_walkers *w, const LaunchArgs &a) {
         CU(cudaFuncSetAttribute(k_walkers<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
     if (w->dw.inj)
-        k_walkers<true><<<grid, block, smem, w->stream>>>(m->dm, w->dw, a);
+        SSE_LAUNCH_KERNEL(k_walkers<true>, grid, block, smem, w->stream, m->dm, w->dw, a);
     else
-        k_walkers<false><<<grid, block, smem, w->stream>>>(m->dm, w->dw, a);
+        SSE_LAUNCH_KERNEL(k_walkers<false>, grid, block, smem, w->stream, m->dm, w->dw, a);
     CU(cudaGetLastError());
     return 0;
 }

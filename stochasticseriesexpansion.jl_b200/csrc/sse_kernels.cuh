@@ -135,11 +135,15 @@ struct Ctx {
     unsigned long long visits;
 };
 
+// The inline-PTX helpers below are the only non-C++ code of this file; the test-only warp emulator
+// (tests/emu/cuda_emu.h) provides host versions and defines SSE_PTX_HELPERS_PROVIDED.
+#ifndef SSE_PTX_HELPERS_PROVIDED
 __device__ __forceinline__ uint32_t lanemask_lt() {
     uint32_t m;
     asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
     return m;
 }
+#endif
 
 template <bool INJ>
 __device__ __forceinline__ uint64_t draw(const Ctx &c, unsigned long long k) {
@@ -522,6 +526,7 @@ struct WormArgs {
     uint32_t maxw, lane, k0, l0, w0, fell, variant;
 };
 
+#ifndef SSE_PTX_HELPERS_PROVIDED
 __device__ __forceinline__ uint4 lds128(uint32_t a) {
     uint4 v;
     asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
@@ -535,6 +540,7 @@ __device__ __forceinline__ double lds_f64(uint32_t a) {
 __device__ __forceinline__ void sts_f64x2(uint32_t a, double x, double y) {
     asm volatile("st.shared.v2.f64 [%0], {%1,%2};" ::"r"(a), "d"(x), "d"(y) : "memory");
 }
+#endif
 
 // uniform doubles for the draws [2*j0, 2*j0 + 64) -> rbuf[64]
 template <bool INJ>
@@ -553,6 +559,7 @@ __device__ __forceinline__ void fill_u01(const WormArgs &a, unsigned long long j
     sts_f64x2(a.rbuf_s + 16u * a.lane, sse_u01(x0), sse_u01(x1));
 }
 
+#ifndef SSE_PTX_HELPERS_PROVIDED
 __device__ __forceinline__ uint4 ldg_cg128(const uint4 *p) {
     uint4 v;
     asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
@@ -562,6 +569,7 @@ __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefe
 __device__ __forceinline__ void stg_u32(void *p, uint32_t v) {
     asm volatile("st.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+#endif
 
 // packed step (t1[].z / outc[].z): bits 1..13 = vertex bits of the op code (diag << 1 | gv << 2),
 // bits 16..17 = exit leg, bits 24..31 = exit worm;  .w: bits 24..31 = dim of the exit leg's site,
