@@ -58,8 +58,8 @@ def build_params(args, n_walkers, walker_id_offset=0, device=-1):
 
 
 def workload_name(args):
-    return (f"2D square-lattice S=1/2 Heisenberg AFM L={args.L}, beta={args.beta}, {args.walkers} walkers per GPU "
-            f"(BASELINE.json configs[1])")
+    cfg = {(32, 32.0): "BASELINE.json configs[1]", (64, 64.0): "BASELINE.json configs[2]"}.get((args.L, args.beta), "custom size")
+    return f"2D square-lattice S=1/2 Heisenberg AFM L={args.L}, beta={args.beta}, {args.walkers} walkers per GPU ({cfg})"
 
 
 def measured_peak():
@@ -219,7 +219,11 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # thermalise (untimed): init! + un-thermalised sweeps (string growth, worm-count controller)
-    wk.init()
+    if args.beta_doublings > 0:
+        # large systems: grow the cold walkers from hot ones (sse_double_beta), then thermalise at the target
+        wk.thermalize_by_beta_doubling(args.beta_doublings, sweeps_per_level=args.therm_per_level)
+    else:
+        wk.init()
     done = 0
     while done < args.therm:
         k = min(50, args.therm - done)
@@ -295,7 +299,7 @@ def run_ours(args):
             "vs_baseline": None, "dtype": "u32/f64", "data": "synthetic",
             "config": {
                 "workload": workload_name(args), "walkers_per_gpu": W, "sweeps_per_step": S,
-                "thermalisation_sweeps": args.therm, "energy_offset_factor": 0.0 if args.deterministic else 0.25,
+                "thermalisation_sweeps": args.therm, "beta_doublings": args.beta_doublings, "energy_offset_factor": 0.0 if args.deterministic else 0.25,
                 "mean_n": sum_n / sweeps, "mean_M": sum_M / sweeps, "visits_per_sweep": visits / sweeps,
                 "l2": "inputs larger than L2: per-GPU walker state %.1f GB >> 126 MB" % (wk.device_bytes() / 1e9),
                 "parallelism": f"walkers sharded over {world} rank(s), no collective inside a sweep",
@@ -343,6 +347,10 @@ def main():
                     help="sweeps per launch (one Carlo bin; the reference tutorial uses binsize 100). Longer launches "
                          "average the per-walker worm-length imbalance: busy fraction 81 %% at 32, 86 %% at 100")
     ap.add_argument("--therm", type=int, default=300)
+    ap.add_argument("--beta-doublings", type=int, default=0,
+                    help="untimed setup: start 2^k times hotter and double beta k times (sse_double_beta) before the "
+                         "--therm sweeps at the target; for L=64, beta=64 use 6")
+    ap.add_argument("--therm-per-level", type=int, default=40, help="sweeps per beta-doubling level")
     ap.add_argument("--deterministic", action="store_true",
                     help="energy_offset_factor=0 tables (the reference's intended but unreachable S=1/2 branch)")
     ap.add_argument("--seed", type=int, default=20261017)

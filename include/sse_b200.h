@@ -163,6 +163,13 @@ int32_t sse_pt_log_weight_ratio(sse_walkers *w, const double *new_T, double *out
 int32_t sse_set_temperature(sse_walkers *w, const double *T /* [n_walkers] */);
 int32_t sse_get_num_operators(sse_walkers *w, int64_t *out /* [n_walkers] */);
 
+/* Thermalisation aid, NOT in the reference (beta doubling): every walker's periodic configuration
+ * (state, S_M) becomes (state, S_M S_M) at temperature T/2 with 2n operators — a valid configuration at the
+ * doubled inverse temperature that is already close to equilibrium, so a cold walker is grown from a cheap
+ * hot one in log2(beta) steps.  Fails loudly (overflow flag) if 2M > m_capacity or 2n > n_capacity.
+ * The caller keeps sweeping with thermalized = 0 afterwards; nothing here touches the random stream. */
+int32_t sse_double_beta(sse_walkers *w);
+
 /* --- parity hooks: run ONE phase on the current configuration with an injected random stream --- */
 /* stream[n_walkers][len]: walker i draws stream[i*len + k]; the stream position restarts at 0.  NULL clears. */
 int32_t sse_set_injected_stream(sse_walkers *w, const uint64_t *stream, int64_t len);

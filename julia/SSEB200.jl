@@ -249,4 +249,12 @@ function Carlo.parallel_tempering_change_parameter!(mc::MC, parameter::Symbol, n
     return nothing
 end
 
+"Thermalisation aid without a reference counterpart (beta doubling) -> sse_double_beta: every walker's string S_M
+becomes S_M S_M at T/2.  Call between unthermalised sweeps; see include/sse_b200.h."
+function double_beta!(mc::MC)
+    check(ccall((:sse_double_beta, libsse), Int32, (Ptr{Cvoid},), mc.hwalkers))
+    mc.T ./= 2
+    return nothing
+end
+
 end # module

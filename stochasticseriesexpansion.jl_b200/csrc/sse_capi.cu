@@ -582,6 +582,17 @@ int32_t sse_set_temperature(sse_walkers *w, const double *T) {
     return 0;
 }
 
+int32_t sse_double_beta(sse_walkers *w) {
+    if (!w) return fail("null handle");
+    if (int32_t s = ensure_committed(w)) return s;
+    CU(cudaSetDevice(w->model->device));
+    const int grid = (w->dw.W + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+    SSE_LAUNCH_KERNEL(k_double_beta, grid, WARPS_PER_CTA * 32, 0, w->stream, w->dw);
+    CU(cudaGetLastError());
+    w->have_vl = false;
+    return sse_sync(w);
+}
+
 int32_t sse_set_injected_stream(sse_walkers *w, const uint64_t *stream, int64_t len) {
     if (!w) return fail("null handle");
     CU(cudaStreamSynchronize(w->stream));

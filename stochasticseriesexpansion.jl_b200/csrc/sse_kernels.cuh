@@ -1035,4 +1035,33 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 7) k_walkers(const DevMode
     }
 }
 
+// ------------------------------------------------------------------------------------------------------
+// beta doubling (thermalisation aid; NOT part of the reference): for a periodic configuration (state, S_M) the
+// doubled string S_M S_M with the same state is a valid configuration at inverse temperature 2*beta with 2n
+// operators, so a cold walker can be grown from a cheap hot one in log2(beta) steps instead of thousands of
+// full-size sweeps.  Needs committed mode.  One warp per walker; M, n double, T halves.
+// ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_double_beta(const DevWalkers dw) {
+    const int w = blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (w >= dw.W) return;
+    const uint32_t fatal = SSE_FLAG_M_OVERFLOW | SSE_FLAG_N_OVERFLOW | SSE_FLAG_STREAM_EXHAUSTED;
+    const uint32_t flags = dw.flags[w];
+    const long long M = dw.M[w], n = dw.n[w];
+    const double T = dw.T[w];
+    __syncwarp();
+    if (flags & fatal) return;
+    if (2 * M > dw.M_cap || 2 * n > dw.n_cap) {
+        if (lane == 0) dw.flags[w] = flags | (2 * M > dw.M_cap ? SSE_FLAG_M_OVERFLOW : SSE_FLAG_N_OVERFLOW);
+        return;
+    }
+    uint32_t *ops = dw.ops + (size_t)w * dw.M_cap;
+    for (long long p = lane; p < M; p += 32) ops[M + p] = ops[p];
+    if (lane == 0) {
+        dw.M[w] = (int)(2 * M);
+        dw.n[w] = (int)(2 * n);
+        dw.T[w] = T * 0.5;
+    }
+}
+
 }  // namespace sse

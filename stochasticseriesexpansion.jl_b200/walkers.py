@@ -175,6 +175,28 @@ class Walkers:
         check(self.L.sse_set_temperature(self.handle, t.ctypes.data_as(f64p)))
         self.T = t
 
+    def double_beta(self):
+        """Thermalisation aid (not in the reference): (state, S_M) -> (state, S_M S_M) at T/2 for every walker."""
+        check(self.L.sse_double_beta(self.handle))
+        self.T = self.T / 2.0
+
+    def thermalize_by_beta_doubling(self, doublings: int, sweeps_per_level: int = 50, final_sweeps: int = 0,
+                                    init_kwargs: dict | None = None):
+        """Reach the target temperatures self.T from 2**doublings times hotter walkers: init! at T*2**doublings, then
+        `sweeps_per_level` unthermalised sweeps and one doubling per level, then `final_sweeps` at the target.
+        The chain that follows is the reference's Markov chain; only its starting point differs from Carlo.init!,
+        so thermalisation sweeps at the target temperature are still the caller's responsibility."""
+        target = self.T.copy()
+        self.set_temperature(target * 2.0 ** doublings)
+        self.init(**(init_kwargs or {}))
+        for _ in range(doublings):
+            self.sweep(sweeps_per_level, thermalized=False)
+            self.double_beta()
+        # T halves exactly (a power of two), so the target is recovered bit for bit
+        assert np.array_equal(self.T, target)
+        if final_sweeps:
+            self.sweep(final_sweeps, thermalized=False)
+
     # --- parity hooks ------------------------------------------------------------------------------
     def set_injected_stream(self, stream):
         if stream is None:

@@ -1,0 +1,128 @@
+"""sse_double_beta (thermalisation aid, not in the reference): the device op against its definition applied to the
+oracle's state — (state, S_M) -> (state, S_M S_M), n -> 2n, T -> T/2 — and the chain that follows, bit for bit.
+Run on the CPU through the warp emulator (tests/emu) and on the GPU (`-m gpu`).  The file sorts last on purpose:
+these GPU tests were written in a session without GPU time."""
+import numpy as np
+import pytest
+
+from helpers import MODEL_CLASSES, isconsistent
+from oracle import OracleWalker
+from sse_b200.capi import SSEError
+from sse_b200.walkers import Walkers
+from test_emu_parity import emu, emu_built  # noqa: F401  (fixtures)
+from test_gpu_parity import _pair, _same_state
+
+
+def _oracle_double(ow):
+    st = ow.get_state()
+    st["operators"] = np.concatenate([st["operators"], st["operators"]])
+    st["num_operators"] *= 2
+    st["T"] /= 2.0
+    ow.set_state(st)
+
+
+def _body_double_beta_parity(name):
+    model = MODEL_CLASSES[name]()
+    dm, om = _pair(model)
+    Ts = np.array([3.2, 1.6, 0.8, 6.4, 2.4])
+    W = len(Ts)
+    gw = Walkers(dm, Ts, m_capacity=8192, seed=31)
+    gw.init()
+    ows = []
+    for i in range(W):
+        ow = OracleWalker(om, float(Ts[i]), seed=31, walker_id=i)
+        ow.init()
+        ows.append(ow)
+    for level in range(3):
+        gw.sweep(6, thermalized=False)
+        gw.double_beta()
+        for i, ow in enumerate(ows):
+            ow.sweep(6, thermalized=False)
+            _oracle_double(ow)
+            a, b = gw.get_state(i), ow.get_state()
+            _same_state(a, b, f"{name} level {level} walker {i}")
+            assert a["T"] == b["T"] == Ts[i] / 2 ** (level + 1)
+            assert isconsistent(b["operators"], b["state"], om.sse_data)
+    assert np.array_equal(gw.T, Ts / 8)
+    gw.sweep(8, thermalized=False)
+    gw.sweep(4, thermalized=True, measure=True)
+    sums, counts = gw.fetch_accumulators()
+    for i, ow in enumerate(ows):
+        ow.sweep(8, thermalized=False)
+        ow.sweep(4, thermalized=True, measure=True)
+        _same_state(gw.get_state(i), ow.get_state(), f"{name} after doubling, walker {i}")
+        osums, ocounts = ow.fetch_accumulators()
+        assert np.array_equal(counts[i], ocounts)
+        np.testing.assert_allclose(sums[i], osums, rtol=1e-12, atol=1e-300)
+
+
+def _body_double_beta_overflow_and_helper():
+    model = MODEL_CLASSES["heisenberg_eof"]()
+    dm, om = _pair(model)
+    gw = Walkers(dm, [0.5, 0.5], m_capacity=256, seed=2)
+    gw.init()
+    gw.sweep(10)
+    with pytest.raises(SSEError):
+        for _ in range(6):  # 2M must outgrow m_capacity = 256 after a few doublings
+            gw.double_beta()
+    # the helper lands exactly on the requested temperatures and leaves consistent configurations
+    target = np.array([0.25, 0.125, 0.2])
+    gw = Walkers(dm, target, m_capacity=8192, seed=5)
+    gw.thermalize_by_beta_doubling(3, sweeps_per_level=5, final_sweeps=5)
+    assert np.array_equal(gw.T, target)
+    for i in range(len(target)):
+        st = gw.get_state(i)
+        assert st["T"] == target[i]
+        assert isconsistent(st["operators"], st["state"], om.sse_data)
+        ow = OracleWalker(om, float(target[i]) * 8, seed=5, walker_id=i)
+        ow.init()
+        for _ in range(3):
+            ow.sweep(5)
+            _oracle_double(ow)
+        ow.sweep(5)
+        _same_state(st, ow.get_state(), f"helper walker {i}")
+
+
+@pytest.mark.parametrize("name", ["heisenberg_eof", "mixed_honeycomb"])
+def test_emu_double_beta_parity(emu, name):
+    _body_double_beta_parity(name)
+
+
+def test_emu_double_beta_overflow_and_helper(emu):
+    _body_double_beta_overflow_and_helper()
+
+
+def test_beta_doubling_starts_close_to_equilibrium():
+    """The point of the aid, checked on the oracle: after log2 steps the operator count is already within a few per
+    cent of the equilibrium value a conventional long thermalisation reaches (4x4 Heisenberg, T = 0.05)."""
+    from oracle import OracleModel
+
+    om = OracleModel(model=MODEL_CLASSES["heisenberg_eof"]())
+    T = 0.05
+    ref = OracleWalker(om, T, seed=9, walker_id=0)
+    ref.init()
+    ref.sweep(3000)
+    ref.sweep(2000, thermalized=True, measure=True)
+    s, c = ref.fetch_accumulators()
+    n_eq = s[1] / c[0]
+    ow = OracleWalker(om, T * 32, seed=9, walker_id=1)
+    ow.init()
+    for _ in range(5):
+        ow.sweep(20)
+        _oracle_double(ow)
+    ow.sweep(20)
+    ow.sweep(2000, thermalized=True, measure=True)
+    s, c = ow.fetch_accumulators()
+    assert abs(s[1] / c[0] - n_eq) < 0.03 * n_eq
+    assert abs(ow.get_state()["num_operators"] - n_eq) < 0.25 * n_eq
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["heisenberg_eof", "spin1_dz", "dimer_bilayer"])
+def test_gpu_double_beta_parity(name):
+    _body_double_beta_parity(name)
+
+
+@pytest.mark.gpu
+def test_gpu_double_beta_overflow_and_helper():
+    _body_double_beta_overflow_and_helper()
