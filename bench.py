@@ -211,6 +211,8 @@ def run_ours(args):
     wk = mc.walkers
     stream = torch.cuda.Stream(device=dev)
     wk.set_stream(stream.cuda_stream)
+    if args.walkers_per_warp != 1:
+        wk.set_walkers_per_warp(args.walkers_per_warp)
 
     def barrier():
         torch.cuda.synchronize()
@@ -298,7 +300,8 @@ def run_ours(args):
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u32/f64", "data": "synthetic",
             "config": {
-                "workload": workload_name(args), "walkers_per_gpu": W, "sweeps_per_step": S,
+                "workload": workload_name(args), "walkers_per_gpu": W, "walkers_per_warp": args.walkers_per_warp,
+                "sweeps_per_step": S,
                 "thermalisation_sweeps": args.therm, "beta_doublings": args.beta_doublings, "energy_offset_factor": 0.0 if args.deterministic else 0.25,
                 "mean_n": sum_n / sweeps, "mean_M": sum_M / sweeps, "visits_per_sweep": visits / sweeps,
                 "l2": "inputs larger than L2: per-GPU walker state %.1f GB >> 126 MB" % (wk.device_bytes() / 1e9),
@@ -306,7 +309,8 @@ def run_ours(args):
             },
             "sweeps_per_s": sweeps / (ms_total * 1e-3),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "traffic_source": tsrc if traffic else None, "peak_source": peak_src, "kernel": "sse::k_walkers<false>",
+                         "traffic": traffic, "traffic_source": tsrc if traffic else None, "peak_source": peak_src,
+                         "kernel": "sse::k_walkers<false>" if args.walkers_per_warp == 1 else "sse::k_walkers_multi<false,%d>" % args.walkers_per_warp,
                          "avg_launch_ms": avg_launch_ms, "algorithmic_bytes_per_launch": b_launch,
                          "formula": "12*M + 16*n + 64*V per walker-sweep (SURVEY.md 8d)"},
             "e2e": {"value": visits2 / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 8 * W,
@@ -343,6 +347,9 @@ def main():
     ap.add_argument("--L", type=int, default=32)
     ap.add_argument("--beta", type=float, default=32.0)
     ap.add_argument("--walkers", type=int, default=4096, help="walkers per GPU")
+    ap.add_argument("--walkers-per-warp", type=int, default=1, choices=[1, 2, 4],
+                    help="launch shape (sse_set_walkers_per_warp): 2 or 4 interleave the worm updates of a warp's walkers; "
+                         "meant for --walkers well beyond 4144 (e.g. --walkers 8192 --walkers-per-warp 2)")
     ap.add_argument("--sweeps-per-step", type=int, default=64,
                     help="sweeps per launch (one Carlo bin; the reference tutorial uses binsize 100). Longer launches "
                          "average the per-walker worm-length imbalance: busy fraction 81 %% at 32, 86 %% at 100")

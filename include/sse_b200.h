@@ -163,6 +163,12 @@ int32_t sse_pt_log_weight_ratio(sse_walkers *w, const double *new_T, double *out
 int32_t sse_set_temperature(sse_walkers *w, const double *T /* [n_walkers] */);
 int32_t sse_get_num_operators(sse_walkers *w, int64_t *out /* [n_walkers] */);
 
+/* Launch shape of sse_sweep, NOT in the reference: how many walkers one warp advances (1, 2 or 4; default 1, or the
+ * environment variable SSE_B200_CHAINS at creation).  With 2 or 4 the worm updates of a warp's walkers are interleaved
+ * so that more dependent load chains are in flight per SM than resident warps; worthwhile for batches well beyond
+ * 4 144 walkers per B200 (28 warps x 148 SMs).  Results do not depend on this setting (bit-identical). */
+int32_t sse_set_walkers_per_warp(sse_walkers *w, int32_t walkers_per_warp);
+
 /* Thermalisation aid, NOT in the reference (beta doubling): every walker's periodic configuration
  * (state, S_M) becomes (state, S_M S_M) at temperature T/2 with 2n operators — a valid configuration at the
  * doubled inverse temperature that is already close to equilibrium, so a cold walker is grown from a cheap

@@ -257,4 +257,8 @@ function double_beta!(mc::MC)
     return nothing
 end
 
+"Launch shape of sweep! without a reference counterpart -> sse_set_walkers_per_warp (1, 2 or 4 walkers per warp)."
+set_walkers_per_warp!(mc::MC, k::Integer) =
+    check(ccall((:sse_set_walkers_per_warp, libsse), Int32, (Ptr{Cvoid}, Int32), mc.hwalkers, k))
+
 end # module

@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "sse_kernels.cuh"
+#include "sse_kernels_multi.cuh"
 
 using namespace sse;
 
@@ -67,6 +68,7 @@ struct sse_walkers {
     DevWalkers dw{};
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    int chains = 1;           // walkers per warp in sse_sweep launches (1 = sse::k_walkers, 2/4 = sse::k_walkers_multi)
     bool indexed = false;     // string currently in indexed mode (after make_vertex_list, before commit)
     bool have_vl = false;
     unsigned long long *d_inj = nullptr;
@@ -91,9 +93,43 @@ int32_t check_flags(sse_walkers *w) {
     return 0;
 }
 
+// walkers per warp -> resident CTAs per SM the multi-chain kernel is compiled for (register budget per thread)
+constexpr int MULTI2_MINB = 7, MULTI4_MINB = 4;
+
+// highest shared-memory level of the multi-chain kernel whose CTA still fits MINB times into an SM (227 KB, 1 KB
+// reserved per CTA); level 0 (rng scratch only) always fits
+int multi_level(const sse_model *m, int ch) {
+    const int minb = ch == 2 ? MULTI2_MINB : MULTI4_MINB;
+    const int budget = 227 * 1024 / minb - 1024;
+    for (int level = 2; level >= 1; --level)
+        if (m->dm.tl.bytes + WARPS_PER_CTA * multi_warp_bytes(m->dm.n_sites, level, ch) <= budget) return level;
+    return 0;
+}
+
+template <bool INJ>
+int32_t launch_multi(sse_walkers *w, const LaunchArgs &a) {
+    const sse_model *m = w->model;
+    const int ch = w->chains;
+    DevWalkers dw = w->dw;
+    dw.smem_state = multi_level(m, ch);
+    if (const char *lv = getenv("SSE_B200_SMEM_LEVEL")) dw.smem_state = std::min(dw.smem_state, std::max(0, atoi(lv)));
+    if (!dw.smem_state && !dw.mark) return fail("internal: mark[] scratch missing for the multi-chain kernel");
+    const int per_cta = WARPS_PER_CTA * ch;
+    const int grid = (dw.W + per_cta - 1) / per_cta;
+    const int block = WARPS_PER_CTA * 32;
+    const size_t smem = (size_t)m->dm.tl.bytes + (size_t)WARPS_PER_CTA * multi_warp_bytes(m->dm.n_sites, dw.smem_state, ch);
+    void (*kern)(const DevModel, const DevWalkers, const LaunchArgs) =
+        ch == 2 ? k_walkers_multi<INJ, 2, MULTI2_MINB> : k_walkers_multi<INJ, 4, MULTI4_MINB>;
+    if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SSE_LAUNCH_KERNEL(kern, grid, block, smem, w->stream, m->dm, dw, a);
+    CU(cudaGetLastError());
+    return 0;
+}
+
 int32_t launch(sse_walkers *w, const LaunchArgs &a) {
     const sse_model *m = w->model;
     CU(cudaSetDevice(m->device));
+    if (a.mode == MODE_SWEEP && w->chains > 1) return w->dw.inj ? launch_multi<true>(w, a) : launch_multi<false>(w, a);
     const int grid = (w->dw.W + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
     const int block = WARPS_PER_CTA * 32;
     const size_t smem = (size_t)m->dm.tl.bytes + (size_t)WARPS_PER_CTA * warp_scratch_bytes(m->dm.n_sites, w->dw.smem_state);
@@ -326,7 +362,9 @@ int32_t sse_walkers_create(const sse_model *m, const sse_walkers_opts *o, sse_wa
     if (m->dm.tl.bytes + WARPS_PER_CTA * warp_scratch_bytes(N, 1) <= 99 * 1024) dw.smem_state = 1;
     if (m->dm.tl.bytes + WARPS_PER_CTA * warp_scratch_bytes(N, 2) <= 32 * 1024) dw.smem_state = 2;
     if (const char *lv = getenv("SSE_B200_SMEM_LEVEL")) dw.smem_state = std::min(dw.smem_state, std::max(0, atoi(lv)));  // tests: force the large-lattice paths
-    if (!dw.smem_state) s |= dev_alloc(w, &dw.mark, (size_t)W * N, true);
+    // global mark[] scratch: needed by whichever kernel (one walker per warp, or 2/4 per warp) runs at level 0
+    if (!dw.smem_state || !multi_level(m, 2) || !multi_level(m, 4) || getenv("SSE_B200_SMEM_LEVEL"))
+        s |= dev_alloc(w, &dw.mark, (size_t)W * N, true);
     s |= dev_alloc(w, &dw.vfirst, (size_t)W * N, false);
     s |= dev_alloc(w, &dw.vlast, (size_t)W * N, false);
     s |= dev_alloc(w, &dw.T, W, true);
@@ -358,7 +396,19 @@ int32_t sse_walkers_create(const sse_model *m, const sse_walkers_opts *o, sse_wa
     CU(cudaMemcpy(dw.last_wlf, wlf.data(), sizeof(double) * W, cudaMemcpyHostToDevice));
     CU(cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking));
     w->own_stream = true;
+    if (const char *ch = getenv("SSE_B200_CHAINS")) {
+        if (sse_set_walkers_per_warp(w, atoi(ch))) { sse_walkers_destroy(w); return 1; }
+    }
     *out = w;
+    return 0;
+}
+
+int32_t sse_set_walkers_per_warp(sse_walkers *w, int32_t walkers_per_warp) {
+    if (!w) return fail("null handle");
+    if (walkers_per_warp != 1 && walkers_per_warp != 2 && walkers_per_warp != 4)
+        return fail("sse_set_walkers_per_warp: supported values are 1, 2 and 4");
+    CU(cudaStreamSynchronize(w->stream));
+    w->chains = walkers_per_warp;
     return 0;
 }
 

@@ -705,43 +705,43 @@ __device__ __forceinline__ uint32_t worm_traverse(const SmTab &st, const DevMode
 // ------------------------------------------------------------------------------------------------------
 // worm_update (src/sse.jl:193-231) incl. worm_traverse! outer (src/sse.jl:233-260).  Needs indexed mode.
 // ------------------------------------------------------------------------------------------------------
+// worm_traverse! outer, start selection (src/sse.jl:241-251): picks the start leg (k0 = record index, l0 = leg) and the
+// worm type w0.  Returns false if the injected stream ran out.
 template <bool INJ>
-__device__ void phase_worm_update(const SmTab &st, const DevModel &dm, const DevWalkers &dw, Ctx &c, bool thermalized,
-                                  int widx) {
-    const uint32_t lane = c.lane, lt = lanemask_lt();
-    const int nworms = (int)ceil(c.num_worms);
-    double total = 1.0;  // sse.jl:194
-    for (int wi = 0; wi < nworms; ++wi) {
-        if (c.n == 0) continue;  // worm_traverse! returns 0 without drawing (sse.jl:234-236)
-        uint32_t k0 = 0, l0 = 0;
-        bool found = false;
-        while (!found) {
-            // rejection loop (sse.jl:241-247): 32 tries evaluated at once, the first success in order wins
-            if (INJ && (long long)c.draws >= c.inj_len) { c.flags |= SSE_FLAG_STREAM_EXHAUSTED; return; }
-            const uint32_t p0 = (uint32_t)sse_uint_below(draw<INJ>(c, c.draws + 2u * lane), (uint64_t)c.M);
-            const uint32_t ll = (uint32_t)sse_uint_below(draw<INJ>(c, c.draws + 2u * lane + 1u), 4u);
-            const uint32_t v = __ldcg(c.ops + p0);
-            const uint32_t ok = __ballot_sync(FULL, v != 0u);
-            if (ok) {
-                const int t = __ffs(ok) - 1;
-                k0 = __shfl_sync(FULL, v, t) - 1u;
-                l0 = __shfl_sync(FULL, ll, t);
-                c.draws += 2u * (unsigned)(t + 1);
-                found = true;
-            } else {
-                c.draws += 64u;
-            }
+__device__ __forceinline__ bool worm_pick_start(const DevModel &dm, Ctx &c, uint32_t &k0, uint32_t &l0, uint32_t &w0) {
+    const uint32_t lane = c.lane;
+    bool found = false;
+    while (!found) {
+        // rejection loop (sse.jl:241-247): 32 tries evaluated at once, the first success in order wins
+        if (INJ && (long long)c.draws >= c.inj_len) { c.flags |= SSE_FLAG_STREAM_EXHAUSTED; return false; }
+        const uint32_t p0 = (uint32_t)sse_uint_below(draw<INJ>(c, c.draws + 2u * lane), (uint64_t)c.M);
+        const uint32_t ll = (uint32_t)sse_uint_below(draw<INJ>(c, c.draws + 2u * lane + 1u), 4u);
+        const uint32_t v = __ldcg(c.ops + p0);
+        const uint32_t ok = __ballot_sync(FULL, v != 0u);
+        if (ok) {
+            const int t = __ffs(ok) - 1;
+            k0 = __shfl_sync(FULL, v, t) - 1u;
+            l0 = __shfl_sync(FULL, ll, t);
+            c.draws += 2u * (unsigned)(t + 1);
+            found = true;
+        } else {
+            c.draws += 64u;
         }
-        const uint4 R0 = __ldcg(c.rec + 2u * k0 + 1u);  // {op code, hints}
-        const uint4 bi = __ldg(dm.bond_info + op_bond(R0.x));
-        const uint32_t dim0 = (l0 & 1u) ? (bi.y >> 24) : (bi.x >> 24);  // site_of_leg (sse.jl:250)
-        const uint32_t w0 = 1u + (uint32_t)sse_uint_below(draw<INJ>(c, c.draws), dim0 - 1u);  // sse.jl:251
-        c.draws += 1;
-        const uint32_t len = worm_traverse<INJ>(st, dm, c, k0, l0, w0);
-        total += (double)len;
-        c.visits += len;
-        if (c.flags & SSE_FLAG_STREAM_EXHAUSTED) return;
     }
+    const uint4 R0 = __ldcg(c.rec + 2u * k0 + 1u);  // {op code, hints}
+    const uint4 bi = __ldg(dm.bond_info + op_bond(R0.x));
+    const uint32_t dim0 = (l0 & 1u) ? (bi.y >> 24) : (bi.x >> 24);  // site_of_leg (sse.jl:250)
+    w0 = 1u + (uint32_t)sse_uint_below(draw<INJ>(c, c.draws), dim0 - 1u);  // sse.jl:251
+    c.draws += 1;
+    return true;
+}
+
+// worm_update after the worms (src/sse.jl:200-228): WormLengthFraction, the worm-count controller, and the state
+// rebuild from the first leg on each site.  total = 1 + sum of the worm lengths (sse.jl:194-198).
+template <bool INJ>
+__device__ __forceinline__ void worm_finish(const SmTab &st, const DevModel &dm, const DevWalkers &dw, Ctx &c, bool thermalized,
+                                            int widx, double total) {
+    const uint32_t lane = c.lane, lt = lanemask_lt();
     if (thermalized && c.n != 0) {  // sse.jl:200-202
         c.last_wlf = total / (double)c.n;
         if (lane == 0) {
@@ -779,6 +779,23 @@ __device__ void phase_worm_update(const SmTab &st, const DevModel &dm, const Dev
     }
     if (INJ && (long long)c.draws > c.inj_len) c.flags |= SSE_FLAG_STREAM_EXHAUSTED;
     __syncwarp();
+}
+
+template <bool INJ>
+__device__ void phase_worm_update(const SmTab &st, const DevModel &dm, const DevWalkers &dw, Ctx &c, bool thermalized,
+                                  int widx) {
+    const int nworms = (int)ceil(c.num_worms);
+    double total = 1.0;  // sse.jl:194
+    for (int wi = 0; wi < nworms; ++wi) {
+        if (c.n == 0) continue;  // worm_traverse! returns 0 without drawing (sse.jl:234-236)
+        uint32_t k0 = 0, l0 = 0, w0 = 0;
+        if (!worm_pick_start<INJ>(dm, c, k0, l0, w0)) return;
+        const uint32_t len = worm_traverse<INJ>(st, dm, c, k0, l0, w0);
+        total += (double)len;
+        c.visits += len;
+        if (c.flags & SSE_FLAG_STREAM_EXHAUSTED) return;
+    }
+    worm_finish<INJ>(st, dm, dw, c, thermalized, widx, total);
 }
 
 // ------------------------------------------------------------------------------------------------------

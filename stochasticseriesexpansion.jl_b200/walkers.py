@@ -175,6 +175,11 @@ class Walkers:
         check(self.L.sse_set_temperature(self.handle, t.ctypes.data_as(f64p)))
         self.T = t
 
+    def set_walkers_per_warp(self, k: int):
+        """Launch shape of sweep(): 1 (default), 2 or 4 walkers per warp with interleaved worm updates.  Results are
+        bit-identical; the setting only matters for throughput of batches beyond ~4144 walkers per B200."""
+        check(self.L.sse_set_walkers_per_warp(self.handle, int(k)))
+
     def double_beta(self):
         """Thermalisation aid (not in the reference): (state, S_M) -> (state, S_M S_M) at T/2 for every walker."""
         check(self.L.sse_double_beta(self.handle))

@@ -86,3 +86,32 @@ def test_emu_api_errors_are_loud(emu):
 @pytest.mark.parametrize("level", [0, 1])
 def test_emu_large_lattice_memory_paths(emu, level, monkeypatch):
     G.test_large_lattice_memory_paths(level, monkeypatch)
+
+
+# ---- 2 and 4 walkers per warp (sse::k_walkers_multi): same trajectories, bit for bit ----------------------------
+@pytest.fixture(params=[2, 4])
+def chains(request, monkeypatch):
+    monkeypatch.setenv("SSE_B200_CHAINS", str(request.param))
+    return request.param
+
+
+@pytest.mark.parametrize("name", ["heisenberg_eof", "mixed_honeycomb"])
+def test_emu_multi_sweep_parity_philox(emu, chains, name):
+    G.test_sweep_parity_philox(name)  # 33 walkers: the last warp is ragged for both 2 and 4 walkers per warp
+
+
+def test_emu_multi_edge_cases_empty_and_ragged_strings(emu, chains):
+    G.test_edge_cases_empty_and_ragged_strings()
+
+
+def test_emu_multi_checkpoint_roundtrip_and_pt_hooks(emu, chains):
+    G.test_checkpoint_roundtrip_and_pt_hooks()
+
+
+def test_emu_multi_overflow_is_loud(emu, chains):
+    G.test_overflow_is_loud()
+
+
+@pytest.mark.parametrize("level", [0, 1])
+def test_emu_multi_large_lattice_memory_paths(emu, chains, level, monkeypatch):
+    G.test_large_lattice_memory_paths(level, monkeypatch)
