@@ -134,6 +134,7 @@ uint64_t collective(int op, uint32_t mask, uint64_t val, int arg, int width) {
 void cta_barrier() {
     Fiber *me = g_cur;
     const uint64_t gen = g_cta.bar_gen;
+    me->bar_gen = gen;
     me->at_bar = true;
     ++g_cta.bar_count;
     if (g_cta.bar_count + g_cta.n_exited == (int)g_cta.f.size()) {
@@ -203,6 +204,8 @@ void run_grid(unsigned grid, unsigned block, size_t smem_bytes, void (*body)(voi
             for (unsigned t = 0; t < block; ++t) {
                 Fiber &f = c.f[t];
                 if (f.done) continue;
+                if (f.arrived && !f.released) continue;            // still waiting for its collective
+                if (f.at_bar && f.bar_gen == c.bar_gen) continue;  // still waiting at __syncthreads
                 g_cur = &f;
                 emu_switch(&c.sched_sp, f.sp);
                 if (f.done) --remaining;

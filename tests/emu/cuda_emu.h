@@ -76,6 +76,7 @@ struct Fiber {
     bool arrived = false, released = false;
     uint64_t result = 0;
     uint32_t ls_mask = 0xffffffffu;  // lanes that execute warp-uniform code together (see lockstep())
+    bool ls_dirty = true;            // a lock-step store happened since this lane's last lock-step barrier
     // __syncthreads
     uint64_t bar_gen = 0;
     bool at_bar = false;
@@ -247,20 +248,28 @@ static inline void sts_f64x2(uint32_t a, double x, double y) {
 // access and the kernel relies on converged code running in lock-step (a lane's load of record k must not see
 // another lane's later store to it).  The hardware does exactly that for converged warps; the emulator gets the
 // same ordering by putting a group barrier in front of each of these accesses.
+// (Loads only need the barrier if a lock-step store happened since the last one; every lane agrees on that.)
 static inline void lockstep() { emu::collective(emu::OP_SYNCWARP, emu::g_cur->ls_mask, 0, 0, 32); }
+static inline void lockstep_load() {
+    if (emu::g_cur->ls_dirty) {
+        lockstep();
+        emu::g_cur->ls_dirty = false;
+    }
+}
 static inline uint4 ldg_cg128(const uint4 *p) {
-    lockstep();
+    lockstep_load();
     emu_check_global(p, 16);
     return *p;
 }
 static inline uint2 ldg_cg64(const uint2 *p) {
-    lockstep();
+    lockstep_load();
     emu_check_global(p, 8);
     return *p;
 }
 static inline void prefetch_l2(const void *) {}
 static inline void stg_u32(void *p, uint32_t v) {
     lockstep();
+    emu::g_cur->ls_dirty = true;
     emu_check_global(p, 4);
     *reinterpret_cast<uint32_t *>(p) = v;
 }

@@ -115,3 +115,12 @@ def test_emu_multi_overflow_is_loud(emu, chains):
 @pytest.mark.parametrize("level", [0, 1])
 def test_emu_multi_large_lattice_memory_paths(emu, chains, level, monkeypatch):
     G.test_large_lattice_memory_paths(level, monkeypatch)
+
+
+# ---- host logic above the C ABI (mc.MC / carlo stand-in / tempering) driven by the emulated kernels ---------------
+def test_emu_mc_carlo_interface_and_checkpoint(emu):
+    G.test_mc_carlo_interface_and_checkpoint()
+
+
+def test_emu_replica_exchange_on_device_walkers(emu):
+    G.test_replica_exchange_on_device_walkers()
