@@ -344,7 +344,8 @@ int32_t sse_walkers_create(const sse_model *m, const sse_walkers_opts *o, sse_wa
     if (o->n_capacity < 64 || o->n_capacity > (1ll << 22)) return fail("sse_walkers_create: n_capacity out of range [64, 2^22]");
     if (o->device >= 0 && o->device != m->device) return fail("sse_walkers_create: model was created on another device");
     CU(cudaSetDevice(m->device));
-    auto w = new sse_walkers();
+    std::unique_ptr<sse_walkers, int32_t (*)(sse_walkers *)> guard(new sse_walkers(), sse_walkers_destroy);  // freed on every error path
+    sse_walkers *w = guard.get();
     w->model = m;
     DevWalkers &dw = w->dw;
     const int W = o->n_walkers, N = m->dm.n_sites;
@@ -380,7 +381,7 @@ int32_t sse_walkers_create(const sse_model *m, const sse_walkers_opts *o, sse_wa
     s |= dev_alloc(w, &dw.counters, 8, true);
     s |= dev_alloc(w, &dw.dbg_len, W, true);
     s |= dev_alloc(w, &dw.obs_out, (size_t)W * dw.n_obs, true);
-    if (s) { sse_walkers_destroy(w); return 1; }
+    if (s) return 1;
     dw.inj = nullptr;
     dw.inj_len = 0;
     dw.seed = o->seed;
@@ -389,7 +390,7 @@ int32_t sse_walkers_create(const sse_model *m, const sse_walkers_opts *o, sse_wa
     dw.atten = o->num_worms_attenuation_factor;
     std::vector<double> T(o->T, o->T + W), nw(W, o->init_num_worms), awl(W, 1.0), wlf(W, NAN);
     for (double t : T)
-        if (!(t > 0)) { sse_walkers_destroy(w); return fail("sse_walkers_create: temperatures must be positive"); }
+        if (!(t > 0)) return fail("sse_walkers_create: temperatures must be positive");
     CU(cudaMemcpy(dw.T, T.data(), sizeof(double) * W, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(dw.num_worms, nw.data(), sizeof(double) * W, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(dw.avg_wl, awl.data(), sizeof(double) * W, cudaMemcpyHostToDevice));
@@ -397,9 +398,9 @@ int32_t sse_walkers_create(const sse_model *m, const sse_walkers_opts *o, sse_wa
     CU(cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking));
     w->own_stream = true;
     if (const char *ch = getenv("SSE_B200_CHAINS")) {
-        if (sse_set_walkers_per_warp(w, atoi(ch))) { sse_walkers_destroy(w); return 1; }
+        if (sse_set_walkers_per_warp(w, atoi(ch))) return 1;
     }
-    *out = w;
+    *out = guard.release();
     return 0;
 }
 
