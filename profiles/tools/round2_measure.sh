@@ -1,0 +1,33 @@
+#!/bin/bash
+# Round-2 first GPU call: everything that was written in round 1 after the GPU budget ran out, measured in one go.
+#   /usr/local/graft/bin/gpurun --timeout 2700 -- 'bash profiles/tools/round2_measure.sh'
+# Outputs land in gpurun_out/r2_*; copy what is to be judged into profiles/ afterwards.
+# Every step runs under its own `timeout`, so a hang in one (new, GPU-untested) kernel cannot take the slot.
+set -u
+cd "${GRAFT_REPO_ROOT:-/root/repo}"
+O=gpurun_out
+mkdir -p $O
+step() { echo "=== $1" | tee -a $O/r2_steps.log; shift; "$@"; echo "rc=$?" | tee -a $O/r2_steps.log; }
+
+# 1. parity gate: the old GPU tests, then the new ones (beta doubling, 2/4 walkers per warp)
+step "pytest gpu (parity, no statistics)" timeout 900 python -m pytest tests -m gpu -x -q --deselect tests/test_gpu_statistics.py \
+     > $O/r2_pytest_parity.log 2>&1
+# 2. default bench line (BASELINE configs[1], one walker per warp)
+step "bench default" timeout 600 python bench.py > $O/r2_bench_default.json 2> $O/r2_bench_default.err
+# 3. more walkers per GPU: two waves of the default kernel vs 2 / 4 walkers per warp
+step "bench 8192 walkers, 1 per warp" timeout 900 python bench.py --walkers 8192 --no-cpu --steps 3 > $O/r2_bench_w8192_k1.json 2> $O/r2_bench_w8192_k1.err
+step "bench 8192 walkers, 2 per warp" timeout 900 python bench.py --walkers 8192 --walkers-per-warp 2 --no-cpu --steps 3 > $O/r2_bench_w8192_k2.json 2> $O/r2_bench_w8192_k2.err
+step "bench 9472 walkers, 4 per warp" timeout 900 python bench.py --walkers 9472 --walkers-per-warp 4 --no-cpu --steps 3 > $O/r2_bench_w9472_k4.json 2> $O/r2_bench_w9472_k4.err
+step "bench 4096 walkers, 2 per warp (expected: no gain)" timeout 600 python bench.py --walkers-per-warp 2 --no-cpu --steps 3 > $O/r2_bench_w4096_k2.json 2> $O/r2_bench_w4096_k2.err
+# 4. BASELINE configs[2]: L = 64, beta = 64, grown by beta doubling
+step "bench L=64 beta=64" timeout 1500 python bench.py --L 64 --beta 64 --walkers 3552 --beta-doublings 6 --therm-per-level 30 --therm 40 \
+     --sweeps-per-step 8 --steps 3 --warmup 3 --cpu-therm 60 --cpu-sweeps 60 > $O/r2_bench_L64.json 2> $O/r2_bench_L64.err
+# 5. ncu: launch list of the default bench command, one full capture of each kernel in the thermalised state
+step "ncu launch list" timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 40 --csv --log-file $O/r2_launches.csv \
+     python bench.py --steps 2 --warmup 3 --therm 100 --sweeps-per-step 4 --no-cpu > $O/r2_ncu_list.log 2>&1
+step "ncu full k_walkers" timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_walkers -s 26 -c 1 -f -o $O/r2_full_k1 \
+     python bench.py --steps 1 --warmup 3 --therm 100 --sweeps-per-step 2 --no-cpu > $O/r2_ncu_full_k1.log 2>&1
+step "ncu full k_walkers_multi" timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_walkers_multi -s 4 -c 1 -f -o $O/r2_full_k2 \
+     python bench.py --walkers 8192 --walkers-per-warp 2 --steps 1 --warmup 3 --therm 100 --sweeps-per-step 2 --no-cpu > $O/r2_ncu_full_k2.log 2>&1
+tail -n 3 $O/r2_pytest_parity.log
+cat $O/r2_steps.log

@@ -1,0 +1,68 @@
+"""One-off soak run (not part of the suite): the emulated kernel source against the oracle over many seeds,
+temperatures, model classes and launch shapes.  Usage: python tests/emu/soak.py [rounds]  ->  one line per case,
+exit code 1 on the first mismatch.  The outcome of the run done in round 1 is recorded in profiles/r1_emu_soak.txt."""
+import os
+import sys
+import time
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
+    sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+from sse_b200 import capi  # noqa: E402
+
+capi.LIB_PATH = os.path.join(HERE, "libsse_b200_emu.so")
+
+from helpers import MODEL_CLASSES  # noqa: E402
+from oracle import OracleModel, OracleWalker  # noqa: E402
+from sse_b200.capi import model_desc_from_model  # noqa: E402
+from sse_b200.walkers import DeviceModel, Walkers  # noqa: E402
+
+
+def main():
+    rounds = int(sys.argv[1]) if len(sys.argv) > 1 else 3
+    rng = np.random.default_rng(2026)
+    t0 = time.time()
+    cases = 0
+    for name, make in MODEL_CLASSES.items():
+        model = make()
+        desc, keep, sd = model_desc_from_model(model)
+        dm = DeviceModel(model=model, desc=desc, keep=keep, sse_data=sd)
+        om = OracleModel(desc=desc, keep=keep, sse_data=sd)
+        for r in range(rounds):
+            for chains in (1, 2, 4):
+                W = int(rng.integers(3, 14))
+                Ts = rng.uniform(0.08, 2.5, size=W)
+                seed = int(rng.integers(1, 2**40))
+                off = int(rng.integers(0, 1000))
+                n_th, n_ms = int(rng.integers(5, 40)), int(rng.integers(1, 12))
+                gw = Walkers(dm, Ts, m_capacity=16384, seed=seed, walker_id_offset=off)
+                gw.set_walkers_per_warp(chains)
+                gw.init()
+                gw.sweep(n_th, thermalized=False)
+                gw.sweep(n_ms, thermalized=True, measure=True)
+                sums, counts = gw.fetch_accumulators()
+                for i in range(W):
+                    ow = OracleWalker(om, float(Ts[i]), seed=seed, walker_id=off + i)
+                    ow.init()
+                    ow.sweep(n_th, thermalized=False)
+                    ow.sweep(n_ms, thermalized=True, measure=True)
+                    a, b = gw.get_state(i), ow.get_state()
+                    ok = (a["num_operators"] == b["num_operators"] and np.array_equal(a["operators"], b["operators"])
+                          and np.array_equal(a["state"], b["state"]) and a["rng_draws"] == b["rng_draws"]
+                          and a["num_worms"] == b["num_worms"])
+                    osums, ocounts = ow.fetch_accumulators()
+                    ok = ok and np.array_equal(counts[i], ocounts) and np.allclose(sums[i], osums, rtol=1e-12, atol=1e-300)
+                    if not ok:
+                        print(f"MISMATCH {name} chains={chains} seed={seed} walker={i} T={Ts[i]}")
+                        sys.exit(1)
+                cases += W
+                print(f"ok {name:16s} chains={chains} walkers={W:2d} sweeps={n_th}+{n_ms} seed={seed}", flush=True)
+    print(f"soak ok: {cases} walker runs bit-identical to the oracle in {time.time() - t0:.0f} s")
+
+
+if __name__ == "__main__":
+    main()
