@@ -1,7 +1,7 @@
 """sse_double_beta (thermalisation aid, not in the reference): the device op against its definition applied to the
 oracle's state — (state, S_M) -> (state, S_M S_M), n -> 2n, T -> T/2 — and the chain that follows, bit for bit.
-Run on the CPU through the warp emulator (tests/emu) and on the GPU (`-m gpu`).  The file sorts last on purpose:
-these GPU tests were written in a session without GPU time."""
+Run on the CPU through the warp emulator (tests/emu) and on the GPU (`-m gpu`).  The file sorts last on purpose: it was
+written when round 1 had two GPU-minutes left (first B200 run: profiles/r1_f_gpu_new_tests.txt, all passed)."""
 import numpy as np
 import pytest
 

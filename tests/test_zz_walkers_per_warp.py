@@ -1,7 +1,7 @@
 """2 and 4 walkers per warp (sse::k_walkers_multi, sse_set_walkers_per_warp): the interleaved worm updates must leave
 every walker on exactly the trajectory of the one-walker-per-warp kernel and of the oracle.  CPU: through the warp
-emulator (tests/emu); GPU: `-m gpu`.  The file sorts last on purpose: its GPU tests were written in a session
-without GPU time."""
+emulator (tests/emu); GPU: `-m gpu`.  The file sorts last on purpose: it was written when
+round 1 had two GPU-minutes left (first B200 run: profiles/r1_f_gpu_new_tests.txt, all passed)."""
 import numpy as np
 import pytest
 
