@@ -35,7 +35,7 @@ def main():
         for r in range(rounds):
             for chains in (1, 2, 4):
                 W = int(rng.integers(3, 14))
-                Ts = rng.uniform(0.08, 2.5, size=W)
+                Ts = rng.uniform(0.15, 2.5, size=W)  # below ~0.1 the S=1 model launches 1e8-visit worms early on
                 seed = int(rng.integers(1, 2**40))
                 off = int(rng.integers(0, 1000))
                 n_th, n_ms = int(rng.integers(5, 40)), int(rng.integers(1, 12))

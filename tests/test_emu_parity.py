@@ -95,8 +95,9 @@ def chains(request, monkeypatch):
     return request.param
 
 
-@pytest.mark.parametrize("name", ["heisenberg_eof", "mixed_honeycomb"])
-def test_emu_multi_sweep_parity_philox(emu, chains, name):
+@pytest.mark.parametrize("k, name", [(2, "mixed_honeycomb"), (4, "heisenberg_eof")])
+def test_emu_multi_sweep_parity_philox(emu, monkeypatch, k, name):
+    monkeypatch.setenv("SSE_B200_CHAINS", str(k))
     G.test_sweep_parity_philox(name)  # 33 walkers: the last warp is ragged for both 2 and 4 walkers per warp
 
 
