@@ -125,3 +125,10 @@ def test_emu_mc_carlo_interface_and_checkpoint(emu):
 
 def test_emu_replica_exchange_on_device_walkers(emu):
     G.test_replica_exchange_on_device_walkers()
+
+
+def test_emu_smoke_entry(emu):
+    """__graft_entry__.smoke()'s own logic (64 walkers x 40 sweeps + estimators vs the oracle), on the emulated kernels."""
+    import __graft_entry__ as g
+
+    g.smoke()
