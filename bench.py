@@ -357,7 +357,8 @@ def main():
     ap.add_argument("--beta-doublings", type=int, default=0,
                     help="untimed setup: start 2^k times hotter and double beta k times (sse_double_beta) before the "
                          "--therm sweeps at the target; for L=64, beta=64 use 6")
-    ap.add_argument("--therm-per-level", type=int, default=40, help="sweeps per beta-doubling level")
+    ap.add_argument("--therm-per-level", type=int, default=10,
+                    help="sweeps per beta-doubling level (run with the controller attenuation 0.1, see Walkers.thermalize_by_beta_doubling)")
     ap.add_argument("--deterministic", action="store_true",
                     help="energy_offset_factor=0 tables (the reference's intended but unreachable S=1/2 branch)")
     ap.add_argument("--seed", type=int, default=20261017)

@@ -169,10 +169,15 @@ int32_t sse_get_num_operators(sse_walkers *w, int64_t *out /* [n_walkers] */);
  * 4 144 walkers per B200 (28 warps x 148 SMs).  Results do not depend on this setting (bit-identical). */
 int32_t sse_set_walkers_per_warp(sse_walkers *w, int32_t walkers_per_warp);
 
+/* The two parameters of the worm-count controller (src/sse.jl:34-35,204-217), changeable between launches.
+ * The reference fixes them in MC(params); a larger attenuation factor during beta doubling lets the controller
+ * follow the quickly growing worm length (see sse_double_beta). */
+int32_t sse_set_controller(sse_walkers *w, double target_worm_length_fraction, double num_worms_attenuation_factor);
+
 /* Thermalisation aid, NOT in the reference (beta doubling): every walker's periodic configuration
  * (state, S_M) becomes (state, S_M S_M) at temperature T/2 with 2n operators — a valid configuration at the
  * doubled inverse temperature that is already close to equilibrium, so a cold walker is grown from a cheap
- * hot one in log2(beta) steps.  Fails loudly (overflow flag) if 2M > m_capacity or 2n > n_capacity.
+ * hot one in log2(beta) steps.  The controller's average worm length doubles as well.  Fails loudly (overflow flag) if 2M > m_capacity or 2n > n_capacity.
  * The caller keeps sweeping with thermalized = 0 afterwards; nothing here touches the random stream. */
 int32_t sse_double_beta(sse_walkers *w);
 

@@ -257,6 +257,11 @@ function double_beta!(mc::MC)
     return nothing
 end
 
+"The controller parameters of MC(params) (src/sse.jl:34-35), changeable at run time -> sse_set_controller."
+set_controller!(mc::MC, target_worm_length_fraction::Real, num_worms_attenuation_factor::Real) =
+    check(ccall((:sse_set_controller, libsse), Int32, (Ptr{Cvoid}, Float64, Float64), mc.hwalkers,
+                target_worm_length_fraction, num_worms_attenuation_factor))
+
 "Launch shape of sweep! without a reference counterpart -> sse_set_walkers_per_warp (1, 2 or 4 walkers per warp)."
 set_walkers_per_warp!(mc::MC, k::Integer) =
     check(ccall((:sse_set_walkers_per_warp, libsse), Int32, (Ptr{Cvoid}, Int32), mc.hwalkers, k))

@@ -151,6 +151,7 @@ def lib():
         "sse_set_temperature": (C.c_int32, [vp, f64p]),
         "sse_get_num_operators": (C.c_int32, [vp, i64p]),
         "sse_double_beta": (C.c_int32, [vp]),
+        "sse_set_controller": (C.c_int32, [vp, C.c_double, C.c_double]),
         "sse_set_walkers_per_warp": (C.c_int32, [vp, C.c_int32]),
         "sse_set_injected_stream": (C.c_int32, [vp, u64p, C.c_int64]),
         "sse_dbg_diagonal_update": (C.c_int32, [vp]),
@@ -174,7 +175,7 @@ EXPORTED_SYMBOLS = [
     "sse_walkers_destroy", "sse_set_stream", "sse_n_observables", "sse_device_bytes", "sse_init", "sse_sweep",
     "sse_sync", "sse_measure", "sse_fetch_accumulators", "sse_accumulators_device_ptr", "sse_fetch_counters",
     "sse_get_state", "sse_set_state", "sse_get_flags", "sse_pt_log_weight_ratio", "sse_set_temperature",
-    "sse_get_num_operators", "sse_double_beta", "sse_set_walkers_per_warp",
+    "sse_get_num_operators", "sse_double_beta", "sse_set_controller", "sse_set_walkers_per_warp",
     "sse_set_injected_stream", "sse_dbg_diagonal_update", "sse_dbg_make_vertex_list",
     "sse_dbg_worm_update", "sse_dbg_worm_traverse", "sse_dbg_get_vertex_list", "sse_dbg_commit",
 ]

@@ -633,6 +633,16 @@ int32_t sse_set_temperature(sse_walkers *w, const double *T) {
     return 0;
 }
 
+int32_t sse_set_controller(sse_walkers *w, double target_worm_length_fraction, double num_worms_attenuation_factor) {
+    if (!w) return fail("null handle");
+    if (!(target_worm_length_fraction > 0) || !(num_worms_attenuation_factor >= 0) || !(num_worms_attenuation_factor <= 1))
+        return fail("sse_set_controller: target_worm_length_fraction must be > 0 and the attenuation factor in [0, 1]");
+    CU(cudaStreamSynchronize(w->stream));
+    w->dw.twlf = target_worm_length_fraction;
+    w->dw.atten = num_worms_attenuation_factor;
+    return 0;
+}
+
 int32_t sse_double_beta(sse_walkers *w) {
     if (!w) return fail("null handle");
     if (int32_t s = ensure_committed(w)) return s;

@@ -1056,7 +1056,8 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 7) k_walkers(const DevMode
 // beta doubling (thermalisation aid; NOT part of the reference): for a periodic configuration (state, S_M) the
 // doubled string S_M S_M with the same state is a valid configuration at inverse temperature 2*beta with 2n
 // operators, so a cold walker can be grown from a cheap hot one in log2(beta) steps instead of thousands of
-// full-size sweeps.  Needs committed mode.  One warp per walker; M, n double, T halves.
+// full-size sweeps.  Needs committed mode.  One warp per walker; M, n and the controller's average worm length double,
+// T halves.
 // ------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_double_beta(const DevWalkers dw) {
     const int w = blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5);
@@ -1065,7 +1066,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_double_beta(const DevWal
     const uint32_t fatal = SSE_FLAG_M_OVERFLOW | SSE_FLAG_N_OVERFLOW | SSE_FLAG_STREAM_EXHAUSTED;
     const uint32_t flags = dw.flags[w];
     const long long M = dw.M[w], n = dw.n[w];
-    const double T = dw.T[w];
+    const double T = dw.T[w], awl = dw.avg_wl[w];
     __syncwarp();
     if (flags & fatal) return;
     if (2 * M > dw.M_cap || 2 * n > dw.n_cap) {
@@ -1078,6 +1079,9 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_double_beta(const DevWal
         dw.M[w] = (int)(2 * M);
         dw.n[w] = (int)(2 * n);
         dw.T[w] = T * 0.5;
+        // worm-count controller (sse.jl:204-217): worms get at least twice as long at twice the inverse temperature;
+        // carrying the old average over would keep num_worms (target = twlf * n / avg_wl) far too high for many sweeps
+        dw.avg_wl[w] = awl * 2.0;
     }
 }
 

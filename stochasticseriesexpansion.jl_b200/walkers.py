@@ -72,6 +72,8 @@ class Walkers:
         o.num_worms_attenuation_factor = num_worms_attenuation_factor
         o.init_num_worms = init_num_worms
         self.m_capacity = o.m_capacity
+        self.target_worm_length_fraction = float(target_worm_length_fraction)
+        self.num_worms_attenuation_factor = float(num_worms_attenuation_factor)
         self.handle = C.c_void_p()
         check(self.L.sse_walkers_create(dmodel.handle, C.byref(o), C.byref(self.handle)))
         self.n_obs = int(self.L.sse_n_observables(self.handle))
@@ -180,23 +182,39 @@ class Walkers:
         bit-identical; the setting only matters for throughput of batches beyond ~4144 walkers per B200."""
         check(self.L.sse_set_walkers_per_warp(self.handle, int(k)))
 
+    def set_controller(self, target_worm_length_fraction: float | None = None, num_worms_attenuation_factor: float | None = None):
+        """The worm-count controller's two parameters (sse.jl:34-35), changeable between launches."""
+        if target_worm_length_fraction is not None:
+            self.target_worm_length_fraction = float(target_worm_length_fraction)
+        if num_worms_attenuation_factor is not None:
+            self.num_worms_attenuation_factor = float(num_worms_attenuation_factor)
+        check(self.L.sse_set_controller(self.handle, self.target_worm_length_fraction, self.num_worms_attenuation_factor))
+
     def double_beta(self):
-        """Thermalisation aid (not in the reference): (state, S_M) -> (state, S_M S_M) at T/2 for every walker."""
+        """Thermalisation aid (not in the reference): (state, S_M) -> (state, S_M S_M) at T/2 for every walker; the
+        controller's average worm length doubles with it."""
         check(self.L.sse_double_beta(self.handle))
         self.T = self.T / 2.0
 
-    def thermalize_by_beta_doubling(self, doublings: int, sweeps_per_level: int = 50, final_sweeps: int = 0,
-                                    init_kwargs: dict | None = None):
+    def thermalize_by_beta_doubling(self, doublings: int, sweeps_per_level: int = 10, final_sweeps: int = 0,
+                                    attenuation: float = 0.1, init_kwargs: dict | None = None):
         """Reach the target temperatures self.T from 2**doublings times hotter walkers: init! at T*2**doublings, then
         `sweeps_per_level` unthermalised sweeps and one doubling per level, then `final_sweeps` at the target.
-        The chain that follows is the reference's Markov chain; only its starting point differs from Carlo.init!,
-        so thermalisation sweeps at the target temperature are still the caller's responsibility."""
+        During the levels the worm-count controller runs with `attenuation` instead of the reference's 0.01 so that it
+        follows the worm length, which grows by more than 2x per level: with 0.01 the worm count stays tuned for the hot
+        levels and the first cold sweeps cost 50x an equilibrium sweep (measured; the reference's own cold start has the
+        same transient).  The chain that follows is the reference's Markov chain; only its starting point and the
+        controller's starting values differ from Carlo.init!, so thermalisation sweeps at the target temperature are
+        still the caller's responsibility."""
         target = self.T.copy()
+        atten0 = self.num_worms_attenuation_factor
         self.set_temperature(target * 2.0 ** doublings)
         self.init(**(init_kwargs or {}))
+        self.set_controller(num_worms_attenuation_factor=attenuation)
         for _ in range(doublings):
             self.sweep(sweeps_per_level, thermalized=False)
             self.double_beta()
+        self.set_controller(num_worms_attenuation_factor=atten0)
         # T halves exactly (a power of two), so the target is recovered bit for bit
         assert np.array_equal(self.T, target)
         if final_sweeps:

@@ -18,6 +18,7 @@ def _oracle_double(ow):
     st["operators"] = np.concatenate([st["operators"], st["operators"]])
     st["num_operators"] *= 2
     st["T"] /= 2.0
+    st["avg_worm_length"] *= 2.0
     ow.set_state(st)
 
 
@@ -74,13 +75,16 @@ def _body_double_beta_overflow_and_helper():
         st = gw.get_state(i)
         assert st["T"] == target[i]
         assert isconsistent(st["operators"], st["state"], om.sse_data)
-        ow = OracleWalker(om, float(target[i]) * 8, seed=5, walker_id=i)
+        # the helper runs the levels with the controller's attenuation factor at 0.1 and the final sweeps at 0.01
+        ow = OracleWalker(om, float(target[i]) * 8, seed=5, walker_id=i, num_worms_attenuation_factor=0.1)
         ow.init()
         for _ in range(3):
             ow.sweep(5)
             _oracle_double(ow)
-        ow.sweep(5)
-        _same_state(st, ow.get_state(), f"helper walker {i}")
+        fw = OracleWalker(om, float(target[i]), seed=5, walker_id=i)
+        fw.set_state(ow.get_state())
+        fw.sweep(5)
+        _same_state(st, fw.get_state(), f"helper walker {i}")
 
 
 @pytest.mark.parametrize("name", ["heisenberg_eof", "mixed_honeycomb"])
