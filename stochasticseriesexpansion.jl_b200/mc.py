@@ -70,8 +70,17 @@ class MC:
 
     # --- Carlo.AbstractMC ----------------------------------------------------------------------
     def init(self, ctx, params: dict):
-        """Carlo.init! (sse.jl:47-60)"""
-        self.walkers.init(int(params.get("init_opstring_cutoff", -1)), int(params.get("diagonal_warmup_sweeps", 5)))
+        """Carlo.init! (sse.jl:47-60).  Optional extension (default off): `beta_doublings = k` starts the walkers 2**k
+        times hotter and grows them with sse_double_beta (`beta_doubling_sweeps` sweeps per level, default 10) before
+        Carlo's own thermalisation sweeps begin."""
+        ik = dict(init_opstring_cutoff=int(params.get("init_opstring_cutoff", -1)),
+                  diagonal_warmup_sweeps=int(params.get("diagonal_warmup_sweeps", 5)))
+        k = int(params.get("beta_doublings", 0))
+        if k > 0:
+            self.walkers.thermalize_by_beta_doubling(k, sweeps_per_level=int(params.get("beta_doubling_sweeps", 10)),
+                                                     init_kwargs=ik)
+        else:
+            self.walkers.init(**ik)
 
     def sweep(self, ctx):
         """Carlo.sweep! (sse.jl:62-68)"""

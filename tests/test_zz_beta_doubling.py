@@ -130,3 +130,33 @@ def test_gpu_double_beta_parity(name):
 @pytest.mark.gpu
 def test_gpu_double_beta_overflow_and_helper():
     _body_double_beta_overflow_and_helper()
+
+
+def _body_mc_init_with_doublings():
+    """MC.init with `beta_doublings` (mc.py): lands on the requested temperature with a consistent, much longer string
+    than Carlo.init! alone would leave, and the Carlo loop runs on from there."""
+    import sse_b200 as S
+    from sse_b200.carlo import MCContext
+    from sse_b200.mc import MC
+
+    params = dict(model=S.MagnetModel, lattice=dict(unitcell=S.UnitCells.chain, size=(8,)), J=1.0, T=0.05, n_walkers=3,
+                  measure=["magnetization"], seed=4, sweeps=10, thermalization=10, binsize=5, beta_doublings=4)
+    mc = MC(params)
+    ctx = MCContext(params)
+    mc.init(ctx, params)
+    assert np.array_equal(mc.walkers.T, np.full(3, 0.05))
+    n = mc.walkers.num_operators()
+    assert np.all(n > 40)  # <n> ~ beta * N_b * 0.7 ~ 110 at beta = 20; Carlo.init! alone leaves ~ N*T*... a handful
+    for _ in range(5):
+        mc.sweep(ctx)
+    st = mc.walkers.get_state(1)
+    assert st["T"] == 0.05 and isconsistent(st["operators"], st["state"], mc.dmodel.sse_data)
+
+
+def test_emu_mc_init_with_doublings(emu):
+    _body_mc_init_with_doublings()
+
+
+@pytest.mark.gpu
+def test_gpu_mc_init_with_doublings():
+    _body_mc_init_with_doublings()
