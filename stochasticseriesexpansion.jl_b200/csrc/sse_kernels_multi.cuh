@@ -54,13 +54,16 @@ struct MultiArgs {
     uint32_t t1_s, outc_s, maxw, lane, variant;
     unsigned long long seed;
     long long inj_len;
-    uint32_t act;  // bit c: chain c is in the middle of a worm
+    uint32_t act;      // bit c: chain c is in the middle of a worm
+    uint32_t closed1;  // out: chains whose worm closed through the first stop test (sse.jl:288-290), which does not count the visit
     uint4 *rec[CH];
     const unsigned long long *inj[CH];
     unsigned long long wid[CH], j0[CH];
     uint32_t rbuf_s[CH], ri[CH];
     uint4 R[CH], H[CH];  // the chain's current record (links, {op code, hints}): already loaded
-    uint32_t pos[CH], wf[CH], len[CH], patch[CH], pval[CH], pos0[CH], w0[CH], fell[CH];
+    uint32_t pos[CH], wf[CH], patch[CH], pval[CH], pos0[CH], w0[CH], fell[CH];
+    unsigned long long draws0[CH];  // stream position at the start of the chase: one draw per visit, so the worm length
+                                    // returned by worm_traverse! is 1 + (draws at the end - draws0) - (closed by stop test 1)
 };
 
 // The interleaved worm_traverse! inner loops (src/sse.jl:274-300) of up to CH walkers.  One iteration = one visit of
@@ -69,25 +72,26 @@ struct MultiArgs {
 // single-chain loop the record registers are reused in place (everything needed from the old record, including the
 // prefetch hint, is taken before the new loads are issued), so no ping-pong copies exist.  Returns the mask of
 // chains whose worm closed; everything else is written back to `a`.
-template <bool INJ, int CH>
+// W1 = every site has dimension 2 (max_worm == 1, e.g. all S = 1/2 models): there is one worm type, so the worm index is not
+// tracked, the transition index needs no worm term and the worm-type halves of both stop tests are constant.
+template <bool INJ, int CH, bool W1>
 __device__ __noinline__ uint32_t worm_multi_loop(MultiArgs<CH> &a) {
-    const uint32_t t1_s = a.t1_s, outc_s = a.outc_s, maxw4 = a.maxw * 4u;
+    const uint32_t t1_s = a.t1_s, outc_s = a.outc_s, maxw4 = W1 ? 4u : a.maxw * 4u;
     const bool pref = !(a.variant & 2u);
     uint4 *rec[CH];
     uint4 R[CH], H[CH];
-    uint32_t pos[CH], wf[CH], len[CH], patch[CH], pval[CH], pos0[CH], w0[CH], ri[CH], rbuf_s[CH], fell = 0;
+    uint32_t pos[CH], wf[CH], patch[CH], pval[CH], pos0[CH], w0[CH], ri[CH], rbuf_s[CH], fell = 0, closed1 = 0;
 #pragma unroll
     for (int c = 0; c < CH; ++c) {
         rec[c] = a.rec[c];
         R[c] = a.R[c];
         H[c] = a.H[c];
         pos[c] = a.pos[c];
-        wf[c] = a.wf[c];
-        len[c] = a.len[c];
+        wf[c] = W1 ? 1u : a.wf[c];
         patch[c] = a.patch[c];
         pval[c] = a.pval[c];
         pos0[c] = a.pos0[c];
-        w0[c] = a.w0[c];
+        w0[c] = W1 ? 1u : a.w0[c];
         ri[c] = a.ri[c];
         rbuf_s[c] = a.rbuf_s[c];
     }
@@ -108,7 +112,7 @@ __device__ __noinline__ uint32_t worm_multi_loop(MultiArgs<CH> &a) {
             const uint32_t p = pos[c];
             const uint32_t x = patch[c] ? pval[c] : H[c].x;
             // transitions[leg_in, worm_in, vi] fused with its first outcome (vertex_data.jl:115-123)
-            uint4 e = lds128(t1_s + 16u * (op_gv(x) * maxw4 + (((wf[c] - 1u) << 2) | (p & 3u))));
+            uint4 e = lds128(t1_s + 16u * (W1 ? ((x & VMASK) | (p & 3u)) : op_gv(x) * maxw4 + (((wf[c] - 1u) << 2) | (p & 3u))));
             if (!(r < __hiloint2double((int)e.y, (int)e.x))) {
                 const uint32_t off = (e.w >> 6) & 0x3ffffu, cnt = e.w & 63u;
                 bool hit = false;
@@ -121,21 +125,24 @@ __device__ __noinline__ uint32_t worm_multi_loop(MultiArgs<CH> &a) {
             const uint32_t leg_out = (e.z >> 16) & 3u;
             const uint32_t posn = rec_sel(R[c], leg_out);  // (leg_in, p) = vertices[leg_out, p] (sse.jl:295)
             const uint32_t hint = rec_link(H[c], leg_out);
-            uint4 *const rn = rec[c] + 2u * (posn >> 2);
+            // record k lives at byte offset 32 k = (link & ~3) << 3, which fits 32 bits (n_capacity <= 2^22): one
+            // 32-bit shift + one 64-bit add per address instead of a 64-bit shift
+            uint8_t *const base = reinterpret_cast<uint8_t *>(rec[c]);
+            const uint4 *const rn = reinterpret_cast<const uint4 *>(base + ((posn & ~3u) << 3));
             R[c] = ldg_cg128(rn);
             H[c] = ldg_cg128(rn + 1);
             // ---- everything below overlaps with the loads (and with the other chains' visits) ----
             const uint32_t newop = (x & ~(VMASK | 2u)) | (e.z & (VMASK | 2u));  // OperCode(bond, new_vertex) (sse.jl:285)
-            stg_u32(rec[c] + 2u * (p >> 2) + 1u, newop);
-            if (pref) prefetch_l2(rec[c] + 2u * (hint >> 2));
-            const uint32_t w_out = e.z >> 24, dim_out = e.w >> 24;
+            stg_u32(base + ((p & ~3u) << 3) + 16u, newop);
+            if (pref) prefetch_l2(base + ((hint & ~3u) << 3));
+            const uint32_t w_out = W1 ? 1u : e.z >> 24, dim_out = W1 ? 2u : e.w >> 24;
             const bool stop1 = (((p & ~3u) | leg_out) == pos0[c]) && (w_out + w0[c] == dim_out);  // sse.jl:288-290
-            len[c] += stop1 ? 0u : 1u;
-            wf[c] = w_out;
+            if (!W1) wf[c] = w_out;
             patch[c] = ((posn >> 2) == (p >> 2)) ? 1u : 0u;  // the link re-enters this record: its load preceded the store
             pval[c] = newop;
             pos[c] = posn;
             const bool stop2 = (posn == pos0[c]) && (w_out == w0[c]);  // sse.jl:297-299
+            if (stop1) closed1 |= 1u << c;
             if (stop1 || stop2) closed |= 1u << c;
         }
     }
@@ -145,12 +152,12 @@ __device__ __noinline__ uint32_t worm_multi_loop(MultiArgs<CH> &a) {
         a.H[c] = H[c];
         a.pos[c] = pos[c];
         a.wf[c] = wf[c];
-        a.len[c] = len[c];
         a.patch[c] = patch[c];
         a.pval[c] = pval[c];
         a.ri[c] = ri[c];
         if ((fell >> c) & 1u) a.fell[c] = 1;
     }
+    a.closed1 = closed1;
     return closed;
 }
 
@@ -252,7 +259,7 @@ __device__ __noinline__ void phase_worm_multi(const SmTab &st, const DevModel &d
             a.w0[ci] = w0;
             a.pos[ci] = a.pos0[ci];
             a.wf[ci] = w0;
-            a.len[ci] = 1;
+            a.draws0[ci] = c.draws;
             a.patch[ci] = 0;
             a.pval[ci] = 0;
             a.fell[ci] = 0;
@@ -278,12 +285,14 @@ __device__ __noinline__ void phase_worm_multi(const SmTab &st, const DevModel &d
         next_worm(ci);
     }
     while (a.act) {
-        const uint32_t closed = worm_multi_loop<INJ, CH>(a);
+        const uint32_t closed = dm.max_worm == 1 ? worm_multi_loop<INJ, CH, true>(a) : worm_multi_loop<INJ, CH, false>(a);
         for (int ci = 0; ci < CH; ++ci) {
             if (!((closed >> ci) & 1u)) continue;
             const int w = mw.w0 + ci;
             // the chain's stream position after the worm; flags
             const unsigned long long draws = 2ull * a.j0[ci] + a.ri[ci];
+            // worm_traverse!'s return value (sse.jl:264,291,302): 1 + visits, the closing visit of stop test 1 not counted
+            const uint32_t len = 1u + (uint32_t)(draws - a.draws0[ci]) - ((a.closed1 >> ci) & 1u);
             uint32_t fl = dw.flags[w];
             if (a.fell[ci]) fl |= SSE_FLAG_SCATTER_FALLTHROUGH;
             if (INJ && (long long)draws > dw.inj_len) fl |= SSE_FLAG_STREAM_EXHAUSTED;
@@ -293,8 +302,8 @@ __device__ __noinline__ void phase_worm_multi(const SmTab &st, const DevModel &d
                 dw.flags[w] = fl;
             }
             __syncwarp();
-            total[ci] += (double)a.len[ci];
-            visits += a.len[ci];
+            total[ci] += (double)len;
+            visits += len;
             if (fl & SSE_FLAG_STREAM_EXHAUSTED) {
                 mw.live &= ~(1u << ci);
                 a.act &= ~(1u << ci);
