@@ -9,7 +9,9 @@
 // every lane still executes every chain uniformly, the chains' record loads are in flight together.
 //
 // The streaming phases (diagonal update + records, hints, commit + estimators) are the single-walker phase functions
-// of sse_kernels.cuh, executed for the warp's walkers one after the other; only the worm phase is interleaved.
+// of sse_kernels.cuh, executed by the whole warp for one walker at a time; only the worm phase is interleaved.  The
+// warp's walkers are not kept in step with each other: each one moves through its own sweeps (multi_run), so the
+// chase always runs over every walker that is in the middle of a worm.
 // Results are bit-identical to the one-walker-per-warp kernel (walkers are independent, and each walker's draws
 // come from its own stream position).
 #pragma once
@@ -227,10 +229,21 @@ __device__ __forceinline__ void multi_close(const DevWalkers &dw, MultiWarp &mw,
     if (c.flags & fatal) mw.live &= ~(1u << ci);
 }
 
-// worm_update (src/sse.jl:193-231) of the warp's live walkers with their worms interleaved.
+// Totals a warp reports at the end of a launch.
+struct MultiStats {
+    unsigned long long visits, sweeps, sum_n, sum_M, cyc_stream, cyc_commit;
+};
+
+// n_sweeps x Carlo.sweep! (src/sse.jl:62-68) for the warp's live walkers.  The walkers are NOT kept in step: each one runs
+// through   diagonal update + records + hints  ->  its worms  ->  worm_finish + commit (+ estimators)   at its own pace.
+// Whenever a walker's worm closes, cold code here decides what it does next (its next worm, or the end of its sweep and
+// the streaming phases of its next one, executed by the whole warp) and then the interleaved chase resumes with every
+// walker that is in the middle of a worm.  So a warp always chases as many chains as it has unfinished walkers, and the
+// spread of worm work per sweep costs nothing until the very end of the launch.
 template <bool INJ, int CH>
-__device__ __noinline__ void phase_worm_multi(const SmTab &st, const DevModel &dm, const DevWalkers &dw, MultiWarp &mw,
-                                              bool thermalized, unsigned long long &visits) {
+__device__ __noinline__ void multi_run(const SmTab &st, const DevModel &dm, const DevWalkers &dw, MultiWarp &mw, int n_sweeps,
+                                       bool thermalized, bool measure, MultiStats &ms) {
+    const uint32_t fatal = SSE_FLAG_M_OVERFLOW | SSE_FLAG_N_OVERFLOW | SSE_FLAG_STREAM_EXHAUSTED;
     MultiArgs<CH> a;
     a.t1_s = (uint32_t)__cvta_generic_to_shared(st.t1);
     a.outc_s = (uint32_t)__cvta_generic_to_shared(st.outc);
@@ -240,17 +253,32 @@ __device__ __noinline__ void phase_worm_multi(const SmTab &st, const DevModel &d
     a.seed = dw.seed;
     a.inj_len = dw.inj_len;
     a.act = 0;
-    int nworms[CH] = {}, wi[CH] = {};
+    a.closed1 = 0;
+    int nworms[CH] = {}, wi[CH] = {}, sweeps_left[CH] = {};
     double total[CH] = {};
-    // start the next worm of chain ci, or retire the chain when it has none left (runtime index: cold code)
-    auto next_worm = [&](int ci) {
+
+    // diagonal_update + make_vertex_list! (+ hints) of walker ci's next sweep; false if the walker hit a fatal flag
+    auto begin_sweep = [&](int ci) -> bool {
+        const long long t0 = clock64();
+        Ctx c = multi_open<INJ, CH>(dm, dw, mw, ci);
+        phase_diag_build<INJ>(st, dm, dw, c, true, true);
+        if (!(c.flags & fatal) && !(dm.variant & 4u)) phase_hints(dm, c);
+        nworms[ci] = (int)ceil(c.num_worms);
+        wi[ci] = 0;
+        total[ci] = 1.0;  // sse.jl:194
+        multi_close(dw, mw, ci, c);
+        ms.cyc_stream += (unsigned long long)(clock64() - t0);
+        return (mw.live >> ci) & 1u;
+    };
+    // start the next worm of walker ci (sets its bit in a.act); false if it has none left or its stream ran out
+    auto next_worm = [&](int ci) -> bool {
         Ctx c = multi_open<INJ, CH>(dm, dw, mw, ci);
         bool started = false;
         while (!started && wi[ci] < nworms[ci]) {
             ++wi[ci];
             if (c.n == 0) continue;  // worm_traverse! returns 0 without drawing (sse.jl:234-236)
             uint32_t k0 = 0, l0 = 0, w0 = 0;
-            if (!worm_pick_start<INJ>(dm, c, k0, l0, w0)) break;  // stream exhausted: flag set, chain retires
+            if (!worm_pick_start<INJ>(dm, c, k0, l0, w0)) break;  // stream exhausted: flag set, the walker retires
             a.rec[ci] = c.rec;
             a.inj[ci] = c.inj;
             a.wid[ci] = c.wid;
@@ -275,21 +303,54 @@ __device__ __noinline__ void phase_worm_multi(const SmTab &st, const DevModel &d
         if (started) a.act |= 1u << ci;
         else a.act &= ~(1u << ci);
         multi_close(dw, mw, ci, c);
+        return started;
     };
+    // the rest of worm_update (sse.jl:200-228), then commit (+ Carlo.measure!) of walker ci's finished sweep
+    auto end_sweep = [&](int ci) {
+        const int w = mw.w0 + ci;
+        Ctx c = multi_open<INJ, CH>(dm, dw, mw, ci);
+        worm_finish<INJ>(st, dm, dw, c, thermalized, w, total[ci]);
+        const long long t0 = clock64();
+        if (!(c.flags & fatal)) {
+            double *out = dw.obs_out + (size_t)w * dw.n_obs;
+            phase_commit_measure(st, dm, dw, c, true, measure, out);
+            ++ms.sweeps;
+            ms.sum_n += (unsigned long long)c.n;
+            ms.sum_M += (unsigned long long)c.M;
+            if (measure) {
+                __syncwarp();
+                for (int i = c.lane; i < dw.n_obs; i += 32)
+                    if (i != SSE_OBS_WORM_LENGTH_FRACTION) dw.acc[(size_t)w * dw.n_obs + i] += out[i];
+                if (c.lane == 0) dw.acc_cnt[2 * w] += 1;
+                __syncwarp();
+            }
+        }
+        multi_close(dw, mw, ci, c);
+        ms.cyc_commit += (unsigned long long)(clock64() - t0);
+    };
+    // drive walker ci until it is in the middle of a worm again, has done all its sweeps, or carries a fatal flag
+    auto advance = [&](int ci) {
+        while ((mw.live >> ci) & 1u) {
+            if (next_worm(ci)) return;
+            if (!((mw.live >> ci) & 1u)) return;  // stream exhausted while picking a start
+            end_sweep(ci);
+            if (!((mw.live >> ci) & 1u)) return;
+            if (--sweeps_left[ci] <= 0) return;
+            if (!begin_sweep(ci)) return;
+        }
+    };
+
     for (int ci = 0; ci < CH; ++ci) {
-        nworms[ci] = 0;
-        wi[ci] = 0;
-        total[ci] = 1.0;  // sse.jl:194
         if (!((mw.live >> ci) & 1u)) continue;
-        nworms[ci] = (int)ceil(dw.num_worms[mw.w0 + ci]);
-        next_worm(ci);
+        sweeps_left[ci] = n_sweeps;
+        if (begin_sweep(ci)) advance(ci);
     }
     while (a.act) {
         const uint32_t closed = dm.max_worm == 1 ? worm_multi_loop<INJ, CH, true>(a) : worm_multi_loop<INJ, CH, false>(a);
         for (int ci = 0; ci < CH; ++ci) {
             if (!((closed >> ci) & 1u)) continue;
             const int w = mw.w0 + ci;
-            // the chain's stream position after the worm; flags
+            // the walker's stream position after the worm; flags
             const unsigned long long draws = 2ull * a.j0[ci] + a.ri[ci];
             // worm_traverse!'s return value (sse.jl:264,291,302): 1 + visits, the closing visit of stop test 1 not counted
             const uint32_t len = 1u + (uint32_t)(draws - a.draws0[ci]) - ((a.closed1 >> ci) & 1u);
@@ -303,20 +364,14 @@ __device__ __noinline__ void phase_worm_multi(const SmTab &st, const DevModel &d
             }
             __syncwarp();
             total[ci] += (double)len;
-            visits += len;
+            ms.visits += len;
+            a.act &= ~(1u << ci);
             if (fl & SSE_FLAG_STREAM_EXHAUSTED) {
                 mw.live &= ~(1u << ci);
-                a.act &= ~(1u << ci);
                 continue;
             }
-            next_worm(ci);
+            advance(ci);
         }
-    }
-    for (int ci = 0; ci < CH; ++ci) {
-        if (!((mw.live >> ci) & 1u)) continue;
-        Ctx c = multi_open<INJ, CH>(dm, dw, mw, ci);
-        worm_finish<INJ>(st, dm, dw, c, thermalized, mw.w0 + ci, total[ci]);
-        multi_close(dw, mw, ci, c);
     }
 }
 
@@ -354,43 +409,10 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MINB) k_walkers_multi(cons
     }
     __syncwarp();
     const uint32_t loaded = mw.live;  // walkers whose state[] is held in shared memory during this launch
-    unsigned long long visits = 0, sweeps = 0, sum_n = 0, sum_M = 0, cyc[3] = {0, 0, 0};
-
-    for (int s = 0; s < a.n_sweeps && mw.live; ++s) {  // Carlo.sweep! (sse.jl:62-68)
-        const long long t0 = clock64();
-        for (int ci = 0; ci < CH; ++ci) {
-            if (!((mw.live >> ci) & 1u)) continue;
-            Ctx c = multi_open<INJ, CH>(dm, dw, mw, ci);
-            phase_diag_build<INJ>(st, dm, dw, c, true, true);
-            if (!(c.flags & fatal) && !(dm.variant & 4u)) phase_hints(dm, c);
-            multi_close(dw, mw, ci, c);
-        }
-        const long long t1 = clock64();
-        phase_worm_multi<INJ, CH>(st, dm, dw, mw, a.thermalized != 0, visits);
-        const long long t2 = clock64();
-        for (int ci = 0; ci < CH; ++ci) {
-            if (!((mw.live >> ci) & 1u)) continue;
-            const int w = mw.w0 + ci;
-            Ctx c = multi_open<INJ, CH>(dm, dw, mw, ci);
-            double *out = dw.obs_out + (size_t)w * dw.n_obs;
-            phase_commit_measure(st, dm, dw, c, true, a.measure != 0, out);
-            ++sweeps;
-            sum_n += (unsigned long long)c.n;
-            sum_M += (unsigned long long)c.M;
-            if (a.measure) {
-                __syncwarp();
-                for (int i = c.lane; i < dw.n_obs; i += 32)
-                    if (i != SSE_OBS_WORM_LENGTH_FRACTION) dw.acc[(size_t)w * dw.n_obs + i] += out[i];
-                if (c.lane == 0) dw.acc_cnt[2 * w] += 1;
-                __syncwarp();
-            }
-            multi_close(dw, mw, ci, c);
-        }
-        const long long t3 = clock64();
-        cyc[0] += (unsigned long long)(t1 - t0);
-        cyc[1] += (unsigned long long)(t2 - t1);
-        cyc[2] += (unsigned long long)(t3 - t2);
-    }
+    MultiStats ms = {0, 0, 0, 0, 0, 0};
+    const long long t_begin = clock64();
+    multi_run<INJ, CH>(st, dm, dw, mw, a.n_sweeps, a.thermalized != 0, a.measure != 0, ms);
+    const unsigned long long cyc_total = (unsigned long long)(clock64() - t_begin);
     __syncwarp();
     if (mw.level)
         for (int ci = 0; ci < CH; ++ci) {
@@ -400,14 +422,15 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MINB) k_walkers_multi(cons
             for (int i = mw.lane; i < N; i += 32) g[i] = s[i];
         }
     if (mw.lane == 0) {
-        if (visits) atomicAdd(dw.counters + 0, visits);
-        if (sweeps) {
-            atomicAdd(dw.counters + 1, sweeps);
-            atomicAdd(dw.counters + 2, sum_n);
-            atomicAdd(dw.counters + 3, sum_M);
-            atomicAdd(dw.counters + 4, cyc[0]);  // SM cycles per phase, per warp (= CH walkers)
-            atomicAdd(dw.counters + 5, cyc[1]);
-            atomicAdd(dw.counters + 6, cyc[2]);
+        if (ms.visits) atomicAdd(dw.counters + 0, ms.visits);
+        if (ms.sweeps) {
+            atomicAdd(dw.counters + 1, ms.sweeps);
+            atomicAdd(dw.counters + 2, ms.sum_n);
+            atomicAdd(dw.counters + 3, ms.sum_M);
+            // SM cycles per phase, per warp (= CH walkers): the worm share is what is left of the launch
+            atomicAdd(dw.counters + 4, ms.cyc_stream);
+            atomicAdd(dw.counters + 5, cyc_total - ms.cyc_stream - ms.cyc_commit);
+            atomicAdd(dw.counters + 6, ms.cyc_commit);
         }
     }
 }
