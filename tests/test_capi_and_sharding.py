@@ -35,6 +35,23 @@ def test_product_path_has_no_oracle_dependency():
                 assert not bad.search(txt), f"{f} depends on the oracle"
 
 
+def test_product_path_never_loads_the_emulator():
+    """tests/emu is test infrastructure: no Python file of the package may name the emulator library, and the only
+    hooks in csrc are the two preprocessor guards the emulator build overrides."""
+    pkg = os.path.join(ROOT, "stochasticseriesexpansion.jl_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            path = os.path.join(dirpath, f)
+            if f.endswith(".py"):
+                assert "emu" not in open(path).read().lower().replace("enumerate", ""), f
+            if f.endswith((".cu", ".cuh")):
+                txt = open(path).read()
+                assert "cuda_emu" not in txt.replace("tests/emu/cuda_emu.h", "") and "#include \"../../tests" not in txt, f
+    from sse_b200 import capi
+
+    assert capi.LIB_PATH.endswith(os.path.join("csrc", "libsse_b200.so"))
+
+
 def test_shard_walkers_partition():
     from sse_b200.sharding import shard_walkers
 
