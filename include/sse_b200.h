@@ -184,6 +184,9 @@ int32_t sse_double_beta(sse_walkers *w);
 /* --- parity hooks: run ONE phase on the current configuration with an injected random stream --- */
 /* stream[n_walkers][len]: walker i draws stream[i*len + k]; the stream position restarts at 0.  NULL clears. */
 int32_t sse_set_injected_stream(sse_walkers *w, const uint64_t *stream, int64_t len);
+/* Tuning switches for A/B timing (speed only, never results; same bits as the environment variable SSE_B200_VARIANT read
+ * at sse_model_create): 2 = no L2 prefetch of the hinted record, 4 = no hint pass.  Takes effect at the next launch. */
+int32_t sse_dbg_set_variant(sse_model *m, uint32_t variant);
 int32_t sse_dbg_diagonal_update(sse_walkers *w);                  /* src/sse.jl:137-191 */
 int32_t sse_dbg_make_vertex_list(sse_walkers *w);                 /* src/vertex_list.jl:15-54 */
 int32_t sse_dbg_worm_update(sse_walkers *w, int32_t thermalized); /* src/sse.jl:193-231; needs a vertex list */

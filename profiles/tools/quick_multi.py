@@ -2,7 +2,8 @@
 """Short device timing of the launch shapes (1 / 2 / 4 walkers per warp) on one thermalised batch, without torch:
 host clock around sse_sweep + sse_sync, work from the device counters.  Written for the last 100 GPU-seconds of
 round 1; every result line is flushed to gpurun_out/ as soon as it exists.
-usage: quick_multi.py L beta walkers doublings sweeps_per_level therm timed_sweeps shapes(e.g. 2,4,1) [out.jsonl]"""
+usage: quick_multi.py L beta walkers doublings sweeps_per_level therm timed_sweeps shapes(e.g. 2,4,1) [out.jsonl] [variants(e.g. 0,2,4)]
+Every (shape, variant) pair is timed on the same batch (variants = sse_dbg_set_variant bits: 2 no prefetch, 4 no hint pass)."""
 import json
 import os
 import sys
@@ -21,6 +22,7 @@ def main():
     L, beta, W, doublings, per_level, therm, timed = [int(x) for x in sys.argv[1:8]]
     shapes = [int(x) for x in sys.argv[8].split(",")]
     out = sys.argv[9] if len(sys.argv) > 9 else os.path.join(ROOT, "gpurun_out", "quick_multi.jsonl")
+    variants = [int(x) for x in sys.argv[10].split(",")] if len(sys.argv) > 10 else [0]
     os.makedirs(os.path.dirname(out), exist_ok=True)
     t_start = time.time()
     model = S.MagnetModel(dict(lattice=dict(unitcell=S.UnitCells.square, size=(L, L)), J=1.0, measure=["magnetization"]))
@@ -30,8 +32,9 @@ def main():
     wk.set_walkers_per_warp(shapes[0])
     wk.thermalize_by_beta_doubling(doublings, sweeps_per_level=per_level, final_sweeps=therm)
     setup = time.time() - t_start
-    for k in shapes:
+    for k, variant in [(k, v) for k in shapes for v in variants]:
         wk.set_walkers_per_warp(k)
+        dm.dbg_set_variant(variant)
         wk.sweep(1, thermalized=True)  # warm-up launch of this shape
         wk.fetch_counters(reset=True)
         t0 = time.perf_counter()
@@ -39,12 +42,12 @@ def main():
         dt = time.perf_counter() - t0
         c = wk.fetch_counters(reset=True)
         cyc = c["cycles_diag_build"] + c["cycles_worm"] + c["cycles_commit_measure"]
-        line = dict(L=L, beta=beta, walkers=W, walkers_per_warp=k, timed_sweeps=timed, seconds=dt,
+        line = dict(L=L, beta=beta, walkers=W, walkers_per_warp=k, variant=variant, timed_sweeps=timed, seconds=dt,
                     visits_per_s=c["visits"] / dt, walker_sweeps_per_s=c["sweeps"] / dt, mean_n=c["sum_n"] / c["sweeps"],
                     mean_M=c["sum_M"] / c["sweeps"], visits_per_sweep=c["visits"] / c["sweeps"],
                     worm_cycle_share=c["cycles_worm"] / max(1, cyc), setup_s=setup,
                     note="host clock around sse_sweep+sse_sync, %d doublings x %d sweeps + %d sweeps thermalisation "
-                         "(worm-count controller not converged: compare shapes, not absolute numbers)" % (doublings, per_level, therm))
+                         "(compare shapes and variants, not absolute numbers)" % (doublings, per_level, therm))
         with open(out, "a") as f:
             f.write(json.dumps(line) + "\n")
         print(json.dumps(line), flush=True)

@@ -154,6 +154,7 @@ def lib():
         "sse_set_controller": (C.c_int32, [vp, C.c_double, C.c_double]),
         "sse_set_walkers_per_warp": (C.c_int32, [vp, C.c_int32]),
         "sse_set_injected_stream": (C.c_int32, [vp, u64p, C.c_int64]),
+        "sse_dbg_set_variant": (C.c_int32, [vp, C.c_uint32]),
         "sse_dbg_diagonal_update": (C.c_int32, [vp]),
         "sse_dbg_make_vertex_list": (C.c_int32, [vp]),
         "sse_dbg_worm_update": (C.c_int32, [vp, C.c_int32]),
@@ -176,7 +177,7 @@ EXPORTED_SYMBOLS = [
     "sse_sync", "sse_measure", "sse_fetch_accumulators", "sse_accumulators_device_ptr", "sse_fetch_counters",
     "sse_get_state", "sse_set_state", "sse_get_flags", "sse_pt_log_weight_ratio", "sse_set_temperature",
     "sse_get_num_operators", "sse_double_beta", "sse_set_controller", "sse_set_walkers_per_warp",
-    "sse_set_injected_stream", "sse_dbg_diagonal_update", "sse_dbg_make_vertex_list",
+    "sse_set_injected_stream", "sse_dbg_set_variant", "sse_dbg_diagonal_update", "sse_dbg_make_vertex_list",
     "sse_dbg_worm_update", "sse_dbg_worm_traverse", "sse_dbg_get_vertex_list", "sse_dbg_commit",
 ]
 

@@ -671,6 +671,12 @@ int32_t sse_set_injected_stream(sse_walkers *w, const uint64_t *stream, int64_t 
     return 0;
 }
 
+int32_t sse_dbg_set_variant(sse_model *m, uint32_t variant) {
+    if (!m) return fail("null handle");
+    m->dm.variant = variant;  // DevModel travels by value with every launch: takes effect at the next one
+    return 0;
+}
+
 int32_t sse_dbg_diagonal_update(sse_walkers *w) {
     if (!w) return fail("null handle");
     if (int32_t s = ensure_committed(w)) return s;

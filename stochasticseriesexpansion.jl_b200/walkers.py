@@ -30,6 +30,10 @@ class DeviceModel:
         self.L = capi.lib()
         check(self.L.sse_model_create(C.byref(desc), C.byref(self.handle)))
 
+    def dbg_set_variant(self, variant: int):
+        """Tuning switches for A/B timing (2 = no hint prefetch, 4 = no hint pass); results never change."""
+        check(self.L.sse_dbg_set_variant(self.handle, int(variant)))
+
     def observable_names(self):
         names = list(OBS_FIXED)
         ests = self.model.get_opstring_estimators() if self.model is not None else []
