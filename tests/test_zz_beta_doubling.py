@@ -160,3 +160,60 @@ def test_emu_mc_init_with_doublings(emu):
 @pytest.mark.gpu
 def test_gpu_mc_init_with_doublings():
     _body_mc_init_with_doublings()
+
+
+def _oracle_thermalize_by_doubling(om, T, seed, wid, doublings, per_level, final):
+    """Walkers.thermalize_by_beta_doubling restated on the oracle (levels at attenuation 0.1, final sweeps at 0.01)."""
+    ow = OracleWalker(om, T * 2 ** doublings, seed=seed, walker_id=wid, num_worms_attenuation_factor=0.1)
+    ow.init()
+    for _ in range(doublings):
+        ow.sweep(per_level)
+        _oracle_double(ow)
+    fw = OracleWalker(om, T, seed=seed, walker_id=wid)
+    fw.set_state(ow.get_state())
+    fw.sweep(final)
+    return fw
+
+
+def _body_full_size_parity(L, beta, doublings, walkers_per_warp):
+    """BASELINE.json configs[1] geometry at full size (2D Heisenberg, L = beta = 32: M ~ 1e5 slots, n ~ 4.6e4 records, worms
+    of ~1e4 visits): thousands of 32-slot chunks per sweep, 18-bit links, hundreds of draw refills per worm —
+    bit for bit against the oracle, reached by beta doubling."""
+    from helpers import heisenberg_square
+
+    model = heisenberg_square(L, False, measure=("magnetization",))
+    dm, om = _pair(model)
+    W = 3
+    T = 1.0 / beta
+    n_est = 0.75 * beta * 2 * L * L
+    gw = Walkers(dm, np.full(W, T), m_capacity=int(3.6 * n_est), n_capacity=int(1.7 * n_est), seed=77)
+    gw.set_walkers_per_warp(walkers_per_warp)
+    gw.thermalize_by_beta_doubling(doublings, sweeps_per_level=4, final_sweeps=2)
+    gw.sweep(2, thermalized=True, measure=True)
+    sums, counts = gw.fetch_accumulators()
+    for i in range(W):
+        fw = _oracle_thermalize_by_doubling(om, T, 77, i, doublings, 4, 2)
+        fw.sweep(2, thermalized=True, measure=True)
+        a, b = gw.get_state(i), fw.get_state()
+        _same_state(a, b, f"full size walker {i}")
+        osums, ocounts = fw.fetch_accumulators()
+        assert np.array_equal(counts[i], ocounts)
+        np.testing.assert_allclose(sums[i], osums, rtol=1e-12, atol=1e-300)
+    assert gw.num_operators().min() > 0.6 * beta * 2 * L * L  # really at full size
+
+
+def test_emu_full_size_parity(emu):
+    """On the emulator the full L = 32 case takes ~3 minutes (passed on 2026-10-17; SSE_B200_SLOW_TESTS=1 repeats it); the
+    default CPU suite runs the same code path at L = 16, beta = 32."""
+    import os
+
+    if os.environ.get("SSE_B200_SLOW_TESTS"):
+        _body_full_size_parity(32, 32, 5, 2)
+    else:
+        _body_full_size_parity(16, 32, 5, 2)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("k", [1, 2, 4])
+def test_gpu_full_size_parity(k):
+    _body_full_size_parity(32, 32, 5, k)
