@@ -132,3 +132,11 @@ def test_emu_smoke_entry(emu):
     import __graft_entry__ as g
 
     g.smoke()
+
+
+def test_emu_reference_dump_replay_machinery(emu):
+    """The replay of julia/dump_golden.jl dumps through the device path (tests/test_reference_dumps.py), self-checked on
+    an oracle-written dump of the same schema, here with the emulated kernels as the device."""
+    import test_reference_dumps as R
+
+    R.test_replay_machinery_selfcheck_gpu()
