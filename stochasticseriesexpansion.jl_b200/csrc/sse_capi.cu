@@ -93,33 +93,53 @@ int32_t check_flags(sse_walkers *w) {
     return 0;
 }
 
-// walkers per warp -> resident CTAs per SM the multi-chain kernel is compiled for (register budget per thread)
+// walkers per warp -> resident CTAs per SM the multi-chain kernel is compiled for (register budget per thread).
+// Tuning only: the environment variable SSE_B200_MULTI_MINB selects one of the other compiled occupancies
+// (2 walkers per warp: 7 or 5 CTAs/SM = 72 or 96 registers; 4 per warp: 4, 5 or 3 CTAs/SM = 128, 96 or 168 registers).
 constexpr int MULTI2_MINB = 7, MULTI4_MINB = 4;
+
+int multi_minb(int ch) {
+    int minb = ch == 2 ? MULTI2_MINB : MULTI4_MINB;
+    if (const char *e = getenv("SSE_B200_MULTI_MINB")) minb = atoi(e);
+    return minb;
+}
 
 // highest shared-memory level of the multi-chain kernel whose CTA still fits MINB times into an SM (227 KB, 1 KB
 // reserved per CTA); level 0 (rng scratch only) always fits
-int multi_level(const sse_model *m, int ch) {
-    const int minb = ch == 2 ? MULTI2_MINB : MULTI4_MINB;
+int multi_level(const sse_model *m, int ch, int minb) {
     const int budget = 227 * 1024 / minb - 1024;
     for (int level = 2; level >= 1; --level)
         if (m->dm.tl.bytes + WARPS_PER_CTA * multi_warp_bytes(m->dm.n_sites, level, ch) <= budget) return level;
     return 0;
 }
 
+typedef void (*multi_kernel_t)(const DevModel, const DevWalkers, const LaunchArgs);
+
+template <bool INJ>
+multi_kernel_t multi_kernel(int ch, int minb) {
+    if (ch == 2 && minb == 7) return k_walkers_multi<INJ, 2, 7>;
+    if (ch == 2 && minb == 5) return k_walkers_multi<INJ, 2, 5>;
+    if (ch == 4 && minb == 4) return k_walkers_multi<INJ, 4, 4>;
+    if (ch == 4 && minb == 5) return k_walkers_multi<INJ, 4, 5>;
+    if (ch == 4 && minb == 3) return k_walkers_multi<INJ, 4, 3>;
+    return nullptr;
+}
+
 template <bool INJ>
 int32_t launch_multi(sse_walkers *w, const LaunchArgs &a) {
     const sse_model *m = w->model;
-    const int ch = w->chains;
+    const int ch = w->chains, minb = multi_minb(ch);
+    multi_kernel_t kern = multi_kernel<INJ>(ch, minb);
+    if (!kern) return fail("SSE_B200_MULTI_MINB: no kernel compiled for " + std::to_string(ch) + " walkers per warp at " +
+                           std::to_string(minb) + " CTAs per SM (available: 2 -> 7, 5;  4 -> 4, 5, 3)");
     DevWalkers dw = w->dw;
-    dw.smem_state = multi_level(m, ch);
+    dw.smem_state = multi_level(m, ch, minb);
     if (const char *lv = getenv("SSE_B200_SMEM_LEVEL")) dw.smem_state = std::min(dw.smem_state, std::max(0, atoi(lv)));
     if (!dw.smem_state && !dw.mark) return fail("internal: mark[] scratch missing for the multi-chain kernel");
     const int per_cta = WARPS_PER_CTA * ch;
     const int grid = (dw.W + per_cta - 1) / per_cta;
     const int block = WARPS_PER_CTA * 32;
     const size_t smem = (size_t)m->dm.tl.bytes + (size_t)WARPS_PER_CTA * multi_warp_bytes(m->dm.n_sites, dw.smem_state, ch);
-    void (*kern)(const DevModel, const DevWalkers, const LaunchArgs) =
-        ch == 2 ? k_walkers_multi<INJ, 2, MULTI2_MINB> : k_walkers_multi<INJ, 4, MULTI4_MINB>;
     if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     SSE_LAUNCH_KERNEL(kern, grid, block, smem, w->stream, m->dm, dw, a);
     CU(cudaGetLastError());
@@ -364,7 +384,7 @@ int32_t sse_walkers_create(const sse_model *m, const sse_walkers_opts *o, sse_wa
     if (m->dm.tl.bytes + WARPS_PER_CTA * warp_scratch_bytes(N, 2) <= 32 * 1024) dw.smem_state = 2;
     if (const char *lv = getenv("SSE_B200_SMEM_LEVEL")) dw.smem_state = std::min(dw.smem_state, std::max(0, atoi(lv)));  // tests: force the large-lattice paths
     // global mark[] scratch: needed by whichever kernel (one walker per warp, or 2/4 per warp) runs at level 0
-    if (!dw.smem_state || !multi_level(m, 2) || !multi_level(m, 4) || getenv("SSE_B200_SMEM_LEVEL"))
+    if (!dw.smem_state || !multi_level(m, 2, 7) || !multi_level(m, 4, 5) || getenv("SSE_B200_SMEM_LEVEL"))
         s |= dev_alloc(w, &dw.mark, (size_t)W * N, true);
     s |= dev_alloc(w, &dw.vfirst, (size_t)W * N, false);
     s |= dev_alloc(w, &dw.vlast, (size_t)W * N, false);

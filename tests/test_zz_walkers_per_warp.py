@@ -112,3 +112,37 @@ def test_gpu_multi_injected_sweeps(k):
 @pytest.mark.gpu
 def test_gpu_multi_switching_keeps_the_trajectory():
     _body_switching_keeps_the_trajectory()
+
+
+def _body_occupancy_variants(monkeypatch):
+    """SSE_B200_MULTI_MINB selects another compiled occupancy of the interleaved kernel (tuning only): same trajectories;
+    a combination that was not compiled is an error, not a silent fallback."""
+    model = MODEL_CLASSES["heisenberg_eof"]()
+    dm, om = G._pair(model)
+    Ts = np.linspace(0.2, 0.9, 6)
+    ref = Walkers(dm, Ts, m_capacity=4096, seed=21)
+    ref.init()
+    ref.sweep(6)
+    for k, minb in ((2, 5), (4, 5), (4, 3)):
+        monkeypatch.setenv("SSE_B200_MULTI_MINB", str(minb))
+        w = Walkers(dm, Ts, m_capacity=4096, seed=21)
+        w.set_walkers_per_warp(k)
+        w.init()
+        w.sweep(6)
+        for i in range(len(Ts)):
+            G._same_state(ref.get_state(i), w.get_state(i), f"{k} per warp at {minb} CTAs/SM, walker {i}")
+    monkeypatch.setenv("SSE_B200_MULTI_MINB", "6")
+    w = Walkers(dm, Ts, m_capacity=4096, seed=21)
+    w.set_walkers_per_warp(2)
+    w.init()
+    with pytest.raises(SSEError):
+        w.sweep(1)
+
+
+def test_emu_multi_occupancy_variants(emu, monkeypatch):
+    _body_occupancy_variants(monkeypatch)
+
+
+@pytest.mark.gpu
+def test_gpu_multi_occupancy_variants(monkeypatch):
+    _body_occupancy_variants(monkeypatch)
