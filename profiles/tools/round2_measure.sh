@@ -37,13 +37,14 @@ if [[ "$STAGE" == *B* ]]; then
 step "bench L=64 beta=64" timeout 1500 python bench.py --L 64 --beta 64 --walkers 3552 --beta-doublings 6 --therm-per-level 10 --therm 60 \
      --sweeps-per-step 8 --steps 3 --warmup 3 --cpu-therm 60 --cpu-sweeps 60 > $O/r2_bench_L64.json 2> $O/r2_bench_L64.err
 # 5. ncu (skip counts: 1 init launch + 300/50 thermalisation launches + 3 warm-up launches precede the timed one)
+#    (k_walkers_multi capture: 5 doubling-level launches + 100/50 thermalisation launches + 3 warm-up launches precede it)
 #    launch list of the default bench command, one full capture of each kernel in the thermalised state
 step "ncu launch list" timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 40 --csv --log-file $O/r2_launches.csv \
      python bench.py --steps 2 --warmup 3 --therm 100 --sweeps-per-step 4 --no-cpu > $O/r2_ncu_list.log 2>&1
 step "ncu full k_walkers" timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_walkers -s 10 -c 1 -f -o $O/r2_full_k1 \
      python bench.py --steps 1 --warmup 3 --therm 300 --sweeps-per-step 2 --no-cpu > $O/r2_ncu_full_k1.log 2>&1
-step "ncu full k_walkers_multi" timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_walkers_multi -s 9 -c 1 -f -o $O/r2_full_k2 \
-     python bench.py --walkers 8192 --walkers-per-warp 2 --steps 1 --warmup 3 --therm 300 --sweeps-per-step 2 --no-cpu > $O/r2_ncu_full_k2.log 2>&1
+step "ncu full k_walkers_multi" timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_walkers_multi -s 10 -c 1 -f -o $O/r2_full_k2 \
+     python bench.py --walkers 8192 --walkers-per-warp 2 --steps 1 --warmup 3 --beta-doublings 5 --therm 100 --sweeps-per-step 2 --no-cpu > $O/r2_ncu_full_k2.log 2>&1
 fi
 tail -n 3 $O/r2_pytest_parity.log 2>/dev/null
 cat $O/r2_steps.log
