@@ -24,11 +24,11 @@ step "bench default" timeout 600 python bench.py > $O/r2_bench_default.json 2> $
 step "bench default workload, doubling setup" timeout 600 python bench.py --beta-doublings 5 --therm 100 --no-cpu --steps 3 > $O/r2_bench_default_doubling.json 2> $O/r2_bench_default_doubling.err
 step "bench 8192 walkers, 1 per warp" timeout 900 python bench.py --walkers 8192 --beta-doublings 5 --therm 100 --no-cpu --steps 3 > $O/r2_bench_w8192_k1.json 2> $O/r2_bench_w8192_k1.err
 step "bench 8192 walkers, 2 per warp" timeout 900 python bench.py --walkers 8192 --walkers-per-warp 2 --beta-doublings 5 --therm 100 --no-cpu --steps 3 > $O/r2_bench_w8192_k2.json 2> $O/r2_bench_w8192_k2.err
-step "bench 9472 walkers, 4 per warp" timeout 900 python bench.py --walkers 9472 --walkers-per-warp 4 --beta-doublings 5 --therm 100 --no-cpu --steps 3 > $O/r2_bench_w9472_k4.json 2> $O/r2_bench_w9472_k4.err
+step "bench 11840 walkers, 4 per warp" timeout 900 python bench.py --walkers 11840 --walkers-per-warp 4 --beta-doublings 5 --therm 100 --no-cpu --steps 3 > $O/r2_bench_w11840_k4.json 2> $O/r2_bench_w11840_k4.err
 step "bench 4096 walkers, 2 per warp (expected: no gain)" timeout 600 python bench.py --walkers-per-warp 2 --beta-doublings 5 --therm 100 --no-cpu --steps 3 > $O/r2_bench_w4096_k2.json 2> $O/r2_bench_w4096_k2.err
 # 3a. other compiled occupancies of the interleaved kernel (SSE_B200_MULTI_MINB)
 step "bench 8192 walkers, 2 per warp, 5 CTAs/SM" env SSE_B200_MULTI_MINB=5 timeout 900 python bench.py --walkers 8192 --walkers-per-warp 2 --beta-doublings 5 --therm 100 --no-cpu --steps 3 > $O/r2_bench_w8192_k2_b5.json 2> $O/r2_bench_w8192_k2_b5.err
-step "bench 11840 walkers, 4 per warp, 5 CTAs/SM" env SSE_B200_MULTI_MINB=5 timeout 900 python bench.py --walkers 11840 --walkers-per-warp 4 --beta-doublings 5 --therm 100 --no-cpu --steps 3 > $O/r2_bench_w11840_k4_b5.json 2> $O/r2_bench_w11840_k4_b5.err
+step "bench 9472 walkers, 4 per warp, 4 CTAs/SM" env SSE_B200_MULTI_MINB=4 timeout 900 python bench.py --walkers 9472 --walkers-per-warp 4 --beta-doublings 5 --therm 100 --no-cpu --steps 3 > $O/r2_bench_w9472_k4_b4.json 2> $O/r2_bench_w9472_k4_b4.err
 # 3b. A/B matrix on one thermalised batch (no torch): shapes x {default, no prefetch, no hint pass}
 step "quick A/B 8192 walkers" timeout 300 python profiles/tools/quick_multi.py 32 32 8192 5 10 60 8 1,2,4 $O/r2_quick_ab.jsonl 0,2,4 > $O/r2_quick_ab.log 2>&1
 fi

@@ -95,8 +95,9 @@ int32_t check_flags(sse_walkers *w) {
 
 // walkers per warp -> resident CTAs per SM the multi-chain kernel is compiled for (register budget per thread).
 // Tuning only: the environment variable SSE_B200_MULTI_MINB selects one of the other compiled occupancies
-// (2 walkers per warp: 7 or 5 CTAs/SM = 72 or 96 registers; 4 per warp: 4, 5 or 3 CTAs/SM = 128, 96 or 168 registers).
-constexpr int MULTI2_MINB = 7, MULTI4_MINB = 4;
+// (2 walkers per warp: 7 (default) or 5 CTAs/SM = 72 or 96 registers; 4 per warp: 5 (default), 4 or 3 CTAs/SM = 96, 128 or
+// 168 registers; the chase loop has no spills in any of them).
+constexpr int MULTI2_MINB = 7, MULTI4_MINB = 5;
 
 int multi_minb(int ch) {
     int minb = ch == 2 ? MULTI2_MINB : MULTI4_MINB;

@@ -123,7 +123,7 @@ def _body_occupancy_variants(monkeypatch):
     ref = Walkers(dm, Ts, m_capacity=4096, seed=21)
     ref.init()
     ref.sweep(6)
-    for k, minb in ((2, 5), (4, 5), (4, 3)):
+    for k, minb in ((2, 5), (4, 4), (4, 3)):
         monkeypatch.setenv("SSE_B200_MULTI_MINB", str(minb))
         w = Walkers(dm, Ts, m_capacity=4096, seed=21)
         w.set_walkers_per_warp(k)
