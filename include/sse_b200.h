@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define SSE_B200_ABI_VERSION 1
+#define SSE_B200_ABI_VERSION 2
 
 /* Flattened `SSEData` + `VertexData` tables + estimator tables.
  * Replaces: SSEData{NSites} (src/sse_data.jl:15-22), VertexData{NSites} (src/vertex_data.jl:13-28),
@@ -73,8 +73,8 @@ typedef struct sse_walkers sse_walkers;
 typedef struct sse_walkers_opts {
     int32_t n_walkers;
     const double *T;                    /* [n_walkers] temperature per walker (params[:T]) */
-    int64_t m_capacity;                 /* capacity of each operator string (slots); M grows inside it */
-    int64_t n_capacity;                 /* capacity of each vertex-record array (non-identity operators) */
+    int64_t m_capacity;                 /* capacity of each operator string (slots); M grows inside it (costs 0.25 B/slot) */
+    int64_t n_capacity;                 /* max non-identity operators per walker, <= 2^22 - 1 (costs 17 B each) */
     int32_t device;                     /* CUDA device ordinal; -1 = current device */
     uint64_t seed;                      /* Philox key */
     uint64_t walker_id_offset;          /* global id of walker 0 (stream id = offset + index) */
@@ -134,9 +134,25 @@ int32_t sse_init(sse_walkers *w, int64_t init_opstring_cutoff, int32_t diagonal_
 /* Carlo.sweep!(mc, ctx) (src/sse.jl:62-68) x n_sweeps for every walker inside ONE persistent launch:
  * diagonal_update -> make_vertex_list! -> worm_update.  `thermalized` = is_thermalized(ctx) (src/sse.jl:139,200,205).
  * If `measure` != 0, Carlo.measure! (src/sse.jl:70-87) runs on the device after every sweep and its
- * observables are added to the per-walker accumulators.  Asynchronous on the handle's stream. */
+ * observables are added to the per-walker accumulators.  Asynchronous on the handle's stream.
+ * Walkers that sse_advance left in the middle of a sweep finish that sweep first (it counts as one of the n_sweeps). */
 int32_t sse_sweep(sse_walkers *w, int32_t n_sweeps, int32_t thermalized, int32_t measure);
 int32_t sse_sync(sse_walkers *w);
+
+/* Free-running form of sse_sweep, NOT in the reference: every walker keeps sweeping until it has completed
+ * `max_sweeps` sweeps or done `visit_budget` worm visits in this call, whichever comes first, and is then parked
+ * wherever it is — between sweeps, between two worms or in the middle of a worm; the next sse_advance / sse_sweep
+ * resumes there.  Each walker still runs exactly the reference's Markov chain (results do not depend on where it was
+ * parked); what changes is that walkers are not kept in step: a launch does the same amount of worm work for every
+ * walker, and one walker inside a very long worm delays nobody else.  Asynchronous on the handle's stream.
+ * sse_get_state, sse_measure, sse_double_beta and the parity hooks need walkers BETWEEN sweeps and fail otherwise
+ * (sse_finish_sweeps completes the sweeps in flight). */
+int32_t sse_advance(sse_walkers *w, int32_t max_sweeps, uint64_t visit_budget, int32_t thermalized, int32_t measure);
+/* Complete the sweeps that sse_advance left in flight (no new sweep is started).  Asynchronous. */
+int32_t sse_finish_sweeps(sse_walkers *w, int32_t thermalized, int32_t measure);
+/* sweeps_done[n_walkers]: completed sweeps since sse_init / sse_set_state; in_flight[n_walkers] (may be NULL): 1 if
+ * the walker is parked inside a sweep. */
+int32_t sse_get_progress(sse_walkers *w, uint64_t *sweeps_done, uint8_t *in_flight);
 
 /* Carlo.measure!(mc, ctx) (src/sse.jl:70-87, 305-376) on the current configuration of every walker:
  * out[n_walkers][n_obs] (host).  Slot 5 holds the last sweep's WormLengthFraction (NaN if none). */
@@ -148,10 +164,27 @@ int32_t sse_fetch_accumulators(sse_walkers *w, double *sums, int64_t *counts, in
 /* Device pointers of the same buffers, for NCCL reductions by the host (no copy). */
 int32_t sse_accumulators_device_ptr(sse_walkers *w, void **sums, void **counts);
 
-/* Totals since creation or the last reset: [0] worm-vertex visits (sum of worm_traverse! lengths,
- * src/sse.jl:302), [1] walker-sweeps, [2] non-identity operators and [3] string slots summed over sweeps,
- * [4..6] SM cycles spent in diagonal-update+vertex-list / worm update / commit+measure summed over walkers, [7] spare. */
-int32_t sse_fetch_counters(sse_walkers *w, uint64_t out[8], int32_t reset);
+/* Totals since creation or the last reset (sse_fetch_counters):
+ *   visits      worm-vertex visits = sum of the lengths returned by worm_traverse! (src/sse.jl:302)
+ *   sweeps      completed walker-sweeps;  sum_n / sum_M: operators / string slots summed over them
+ *   cyc_build / cyc_finish / cyc_idle   SM cycles of the stream warps in diagonal update + record build / end of
+ *               worm_update + measure / waiting for work;   tasks: streaming tasks
+ *   cyc_worm    SM cycles of the worm warps;  lane_iters: visits they executed;  warp_iters: loop iterations they
+ *               issued (lane_iters / (32 * warp_iters) = share of lanes with a walker to chase) */
+#define SSE_CNT_VISITS 0
+#define SSE_CNT_SWEEPS 1
+#define SSE_CNT_SUM_N 2
+#define SSE_CNT_SUM_M 3
+#define SSE_CNT_CYC_BUILD 4
+#define SSE_CNT_CYC_WORM 5
+#define SSE_CNT_CYC_FINISH 6
+#define SSE_CNT_CYC_IDLE 7
+#define SSE_CNT_LANE_ITERS 8
+#define SSE_CNT_WARP_ITERS 9
+#define SSE_CNT_TASKS 10
+#define SSE_CNT_ANY_FATAL 15 /* internal: some walker raised a fatal flag */
+#define SSE_N_COUNTERS 16
+int32_t sse_fetch_counters(sse_walkers *w, uint64_t out[SSE_N_COUNTERS], int32_t reset);
 
 /* Carlo.write_checkpoint / read_checkpoint (src/sse.jl:89-107). */
 int32_t sse_get_state(sse_walkers *w, int32_t walker, sse_walker_state *st);
@@ -163,11 +196,11 @@ int32_t sse_pt_log_weight_ratio(sse_walkers *w, const double *new_T, double *out
 int32_t sse_set_temperature(sse_walkers *w, const double *T /* [n_walkers] */);
 int32_t sse_get_num_operators(sse_walkers *w, int64_t *out /* [n_walkers] */);
 
-/* Launch shape of sse_sweep, NOT in the reference: how many walkers one warp advances (1, 2 or 4; default 1, or the
- * environment variable SSE_B200_CHAINS at creation).  With 2 or 4 the worm updates of a warp's walkers are interleaved
- * so that more dependent load chains are in flight per SM than resident warps; worthwhile for batches well beyond
- * 4 144 walkers per B200 (28 warps x 148 SMs).  Results do not depend on this setting (bit-identical). */
-int32_t sse_set_walkers_per_warp(sse_walkers *w, int32_t walkers_per_warp);
+/* Launch shape of sse_sweep / sse_advance, NOT in the reference: warps per CTA that chase worms (one lane = one
+ * walker) and warps that run the streaming phases (one warp = one walker); one CTA per SM.  0 = choose automatically
+ * from the number of walkers (default; environment SSE_B200_WORM_WARPS / SSE_B200_STREAM_WARPS at creation).
+ * worm_warps + stream_warps <= 24.  Results do not depend on this setting (bit-identical). */
+int32_t sse_set_launch_shape(sse_walkers *w, int32_t worm_warps, int32_t stream_warps);
 
 /* The two parameters of the worm-count controller (src/sse.jl:34-35,204-217), changeable between launches.
  * The reference fixes them in MC(params); a larger attenuation factor during beta doubling lets the controller
@@ -184,9 +217,6 @@ int32_t sse_double_beta(sse_walkers *w);
 /* --- parity hooks: run ONE phase on the current configuration with an injected random stream --- */
 /* stream[n_walkers][len]: walker i draws stream[i*len + k]; the stream position restarts at 0.  NULL clears. */
 int32_t sse_set_injected_stream(sse_walkers *w, const uint64_t *stream, int64_t len);
-/* Tuning switches for A/B timing (speed only, never results; same bits as the environment variable SSE_B200_VARIANT read
- * at sse_model_create): 2 = no L2 prefetch of the hinted record, 4 = no hint pass.  Takes effect at the next launch. */
-int32_t sse_dbg_set_variant(sse_model *m, uint32_t variant);
 int32_t sse_dbg_diagonal_update(sse_walkers *w);                  /* src/sse.jl:137-191 */
 int32_t sse_dbg_make_vertex_list(sse_walkers *w);                 /* src/vertex_list.jl:15-54 */
 int32_t sse_dbg_worm_update(sse_walkers *w, int32_t thermalized); /* src/sse.jl:193-231; needs a vertex list */
@@ -197,8 +227,6 @@ int32_t sse_dbg_worm_traverse(sse_walkers *w, int32_t l0, int64_t p0, int32_t wo
  * v_first/v_last[n_sites][2].  Valid after sse_dbg_make_vertex_list / before the next sweep. */
 int32_t sse_dbg_get_vertex_list(sse_walkers *w, int32_t walker, int64_t *vertices, int64_t m_len,
                                 int64_t *v_first, int64_t *v_last);
-/* Commit the worm phase's vertex changes back into the operator string (done automatically by sse_sweep). */
-int32_t sse_dbg_commit(sse_walkers *w);
 
 #ifdef __cplusplus
 }

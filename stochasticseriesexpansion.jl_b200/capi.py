@@ -152,15 +152,16 @@ def lib():
         "sse_get_num_operators": (C.c_int32, [vp, i64p]),
         "sse_double_beta": (C.c_int32, [vp]),
         "sse_set_controller": (C.c_int32, [vp, C.c_double, C.c_double]),
-        "sse_set_walkers_per_warp": (C.c_int32, [vp, C.c_int32]),
+        "sse_set_launch_shape": (C.c_int32, [vp, C.c_int32, C.c_int32]),
+        "sse_advance": (C.c_int32, [vp, C.c_int32, C.c_uint64, C.c_int32, C.c_int32]),
+        "sse_finish_sweeps": (C.c_int32, [vp, C.c_int32, C.c_int32]),
+        "sse_get_progress": (C.c_int32, [vp, u64p, u8p]),
         "sse_set_injected_stream": (C.c_int32, [vp, u64p, C.c_int64]),
-        "sse_dbg_set_variant": (C.c_int32, [vp, C.c_uint32]),
         "sse_dbg_diagonal_update": (C.c_int32, [vp]),
         "sse_dbg_make_vertex_list": (C.c_int32, [vp]),
         "sse_dbg_worm_update": (C.c_int32, [vp, C.c_int32]),
         "sse_dbg_worm_traverse": (C.c_int32, [vp, C.c_int32, C.c_int64, C.c_int32, i64p]),
         "sse_dbg_get_vertex_list": (C.c_int32, [vp, C.c_int32, i64p, C.c_int64, i64p, i64p]),
-        "sse_dbg_commit": (C.c_int32, [vp]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)  # AttributeError if the symbol is missing
@@ -176,9 +177,10 @@ EXPORTED_SYMBOLS = [
     "sse_walkers_destroy", "sse_set_stream", "sse_n_observables", "sse_device_bytes", "sse_init", "sse_sweep",
     "sse_sync", "sse_measure", "sse_fetch_accumulators", "sse_accumulators_device_ptr", "sse_fetch_counters",
     "sse_get_state", "sse_set_state", "sse_get_flags", "sse_pt_log_weight_ratio", "sse_set_temperature",
-    "sse_get_num_operators", "sse_double_beta", "sse_set_controller", "sse_set_walkers_per_warp",
-    "sse_set_injected_stream", "sse_dbg_set_variant", "sse_dbg_diagonal_update", "sse_dbg_make_vertex_list",
-    "sse_dbg_worm_update", "sse_dbg_worm_traverse", "sse_dbg_get_vertex_list", "sse_dbg_commit",
+    "sse_get_num_operators", "sse_double_beta", "sse_set_controller", "sse_set_launch_shape",
+    "sse_advance", "sse_finish_sweeps", "sse_get_progress",
+    "sse_set_injected_stream", "sse_dbg_diagonal_update", "sse_dbg_make_vertex_list",
+    "sse_dbg_worm_update", "sse_dbg_worm_traverse", "sse_dbg_get_vertex_list",
 ]
 
 

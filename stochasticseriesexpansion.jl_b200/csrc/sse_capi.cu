@@ -1,8 +1,9 @@
-// sse_capi.cu — C ABI of libsse_b200.so (include/sse_b200.h): table flattening to the device image,
-// device memory ownership, launches of the one walker kernel (sse_kernels.cuh), checkpoint conversion
-// between the device op codes and the reference's UInt64 OperCode layout (src/opercode.jl:43-47).
+// sse_capi.cu — C ABI of libsse_b200.so (include/sse_b200.h): table flattening to the device image, device memory
+// ownership, launches of the kernels (sse_sweep.cuh), checkpoint conversion between the device layout (occupancy
+// bitmap + record ring) and the reference's UInt64 OperCode strings (src/opercode.jl:43-47).
 // No CPU fallback exists: every entry point runs on the GPU or returns an error status.
 #include <cmath>
+#include <cstddef>
 #include <cstdio>
 #include <algorithm>
 #include <cstdlib>
@@ -11,8 +12,7 @@
 #include <string>
 #include <vector>
 
-#include "sse_kernels.cuh"
-#include "sse_kernels_multi.cuh"
+#include "sse_sweep.cuh"
 
 using namespace sse;
 
@@ -51,6 +51,7 @@ cudaError_t upload(T **dst, const std::vector<T> &v) {
 
 struct sse_model {
     int device = 0;
+    int n_sm = 1;
     DevModel dm{};
     // host copies for checkpoint conversion and validation
     std::vector<int32_t> bond_type, bond_sites, type_vertex_off;
@@ -68,9 +69,9 @@ struct sse_walkers {
     DevWalkers dw{};
     cudaStream_t stream = nullptr;
     bool own_stream = false;
-    int chains = 1;           // walkers per warp in sse_sweep launches (1 = sse::k_walkers, 2/4 = sse::k_walkers_multi)
-    bool indexed = false;     // string currently in indexed mode (after make_vertex_list, before commit)
-    bool have_vl = false;
+    int worm_warps = 0, stream_warps = 0;  // launch shape of k_sweep; 0 = automatic
+    bool have_vl = false;                  // leg links valid (parity hooks)
+    bool maybe_in_flight = false;          // sse_advance may have parked walkers inside a sweep
     unsigned long long *d_inj = nullptr;
     int64_t bytes = 0;
     std::vector<void *> allocs;
@@ -78,91 +79,129 @@ struct sse_walkers {
 
 namespace {
 
-int32_t check_flags(sse_walkers *w) {
-    std::vector<uint32_t> f(w->dw.W);
-    CU(cudaMemcpyAsync(f.data(), w->dw.flags, sizeof(uint32_t) * f.size(), cudaMemcpyDeviceToHost, w->stream));
+// ---- strided access to one field of the per-walker control blocks ----
+template <class T>
+int32_t get_field(sse_walkers *w, size_t offset, std::vector<T> &out) {
+    out.resize(w->dw.W);
+    CU(cudaMemcpy2DAsync(out.data(), sizeof(T), reinterpret_cast<const char *>(w->dw.ctl) + offset, sizeof(WalkerCtl), sizeof(T),
+                         (size_t)w->dw.W, cudaMemcpyDeviceToHost, w->stream));
     CU(cudaStreamSynchronize(w->stream));
+    return 0;
+}
+template <class T>
+int32_t set_field(sse_walkers *w, size_t offset, const T *src) {
+    CU(cudaMemcpy2DAsync(reinterpret_cast<char *>(w->dw.ctl) + offset, sizeof(WalkerCtl), src, sizeof(T), sizeof(T), (size_t)w->dw.W,
+                         cudaMemcpyHostToDevice, w->stream));
+    CU(cudaStreamSynchronize(w->stream));
+    return 0;
+}
+#define CTL_OFF(f) offsetof(WalkerCtl, f)
+
+int32_t check_flags(sse_walkers *w) {
+    unsigned long long any = 0;
+    CU(cudaMemcpyAsync(&any, w->dw.counters + SSE_CNT_ANY_FATAL, sizeof(any), cudaMemcpyDeviceToHost, w->stream));
+    CU(cudaStreamSynchronize(w->stream));
+    if (!any) return 0;
+    std::vector<uint32_t> f;
+    if (int32_t s = get_field(w, CTL_OFF(flags), f)) return s;
     for (int i = 0; i < w->dw.W; ++i) {
         if (f[i] & SSE_FLAG_M_OVERFLOW)
-            return fail("walker " + std::to_string(i) + ": operator string outgrew m_capacity (recreate with a larger m_capacity)");
+            return fail("walker " + std::to_string(i) + ": operator string outgrew m_capacity (recreate with a larger m_capacity, or sse_grow_capacity)");
         if (f[i] & SSE_FLAG_N_OVERFLOW)
-            return fail("walker " + std::to_string(i) + ": more operators than n_capacity (recreate with a larger n_capacity)");
+            return fail("walker " + std::to_string(i) + ": more operators than n_capacity (recreate with a larger n_capacity, or sse_grow_capacity)");
         if (f[i] & SSE_FLAG_STREAM_EXHAUSTED)
             return fail("walker " + std::to_string(i) + ": injected random stream exhausted");
     }
     return 0;
 }
 
-// walkers per warp -> resident CTAs per SM the multi-chain kernel is compiled for (register budget per thread).
-// Tuning only: the environment variable SSE_B200_MULTI_MINB selects one of the other compiled occupancies
-// (2 walkers per warp: 7 (default) or 5 CTAs/SM = 72 or 96 registers; 4 per warp: 5 (default), 4 or 3 CTAs/SM = 96, 128 or
-// 168 registers; the chase loop has no spills in any of them).
-constexpr int MULTI2_MINB = 7, MULTI4_MINB = 5;
-
-int multi_minb(int ch) {
-    int minb = ch == 2 ? MULTI2_MINB : MULTI4_MINB;
-    if (const char *e = getenv("SSE_B200_MULTI_MINB")) minb = atoi(e);
-    return minb;
+// shared-memory level of the streaming warps: 1 = state[N] + mark[N] in shared memory, 0 = in global memory
+int phase_level(const sse_model *m) {
+    int level = (m->dm.tl.bytes + PHASE_WARPS * stream_scratch_bytes(m->dm.n_sites, 1) <= 99 * 1024) ? 1 : 0;
+    if (const char *lv = getenv("SSE_B200_SMEM_LEVEL")) level = std::min(level, std::max(0, atoi(lv)));
+    return level;
 }
 
-// highest shared-memory level of the multi-chain kernel whose CTA still fits MINB times into an SM (227 KB, 1 KB
-// reserved per CTA); level 0 (rng scratch only) always fits
-int multi_level(const sse_model *m, int ch, int minb) {
-    const int budget = 227 * 1024 / minb - 1024;
-    for (int level = 2; level >= 1; --level)
-        if (m->dm.tl.bytes + WARPS_PER_CTA * multi_warp_bytes(m->dm.n_sites, level, ch) <= budget) return level;
-    return 0;
-}
-
-typedef void (*multi_kernel_t)(const DevModel, const DevWalkers, const LaunchArgs);
-
-template <bool INJ>
-multi_kernel_t multi_kernel(int ch, int minb) {
-    if (ch == 2 && minb == 7) return k_walkers_multi<INJ, 2, 7>;
-    if (ch == 2 && minb == 5) return k_walkers_multi<INJ, 2, 5>;
-    if (ch == 4 && minb == 4) return k_walkers_multi<INJ, 4, 4>;
-    if (ch == 4 && minb == 5) return k_walkers_multi<INJ, 4, 5>;
-    if (ch == 4 && minb == 3) return k_walkers_multi<INJ, 4, 3>;
-    return nullptr;
-}
-
-template <bool INJ>
-int32_t launch_multi(sse_walkers *w, const LaunchArgs &a) {
-    const sse_model *m = w->model;
-    const int ch = w->chains, minb = multi_minb(ch);
-    multi_kernel_t kern = multi_kernel<INJ>(ch, minb);
-    if (!kern) return fail("SSE_B200_MULTI_MINB: no kernel compiled for " + std::to_string(ch) + " walkers per warp at " +
-                           std::to_string(minb) + " CTAs per SM (available: 2 -> 7, 5;  4 -> 4, 5, 3)");
-    DevWalkers dw = w->dw;
-    dw.smem_state = multi_level(m, ch, minb);
-    if (const char *lv = getenv("SSE_B200_SMEM_LEVEL")) dw.smem_state = std::min(dw.smem_state, std::max(0, atoi(lv)));
-    if (!dw.smem_state && !dw.mark) return fail("internal: mark[] scratch missing for the multi-chain kernel");
-    const int per_cta = WARPS_PER_CTA * ch;
-    const int grid = (dw.W + per_cta - 1) / per_cta;
-    const int block = WARPS_PER_CTA * 32;
-    const size_t smem = (size_t)m->dm.tl.bytes + (size_t)WARPS_PER_CTA * multi_warp_bytes(m->dm.n_sites, dw.smem_state, ch);
-    if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    SSE_LAUNCH_KERNEL(kern, grid, block, smem, w->stream, m->dm, dw, a);
-    CU(cudaGetLastError());
-    return 0;
-}
-
-int32_t launch(sse_walkers *w, const LaunchArgs &a) {
+int32_t launch_phase(sse_walkers *w, PhaseArgs a) {
     const sse_model *m = w->model;
     CU(cudaSetDevice(m->device));
-    if (a.mode == MODE_SWEEP && w->chains > 1) return w->dw.inj ? launch_multi<true>(w, a) : launch_multi<false>(w, a);
-    const int grid = (w->dw.W + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
-    const int block = WARPS_PER_CTA * 32;
-    const size_t smem = (size_t)m->dm.tl.bytes + (size_t)WARPS_PER_CTA * warp_scratch_bytes(m->dm.n_sites, w->dw.smem_state);
+    a.level = phase_level(m);
+    if (!a.level && !w->dw.mark) return fail("internal: mark[] scratch missing");
+    const int grid = (w->dw.W + PHASE_WARPS - 1) / PHASE_WARPS;
+    const size_t smem = (size_t)m->dm.tl.bytes + (size_t)PHASE_WARPS * stream_scratch_bytes(m->dm.n_sites, a.level);
     if (smem > 48 * 1024) {
-        CU(cudaFuncSetAttribute(k_walkers<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CU(cudaFuncSetAttribute(k_walkers<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CU(cudaFuncSetAttribute(k_phase<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CU(cudaFuncSetAttribute(k_phase<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
     if (w->dw.inj)
-        SSE_LAUNCH_KERNEL(k_walkers<true>, grid, block, smem, w->stream, m->dm, w->dw, a);
+        SSE_LAUNCH_KERNEL(k_phase<true>, grid, PHASE_WARPS * 32, smem, w->stream, m->dm, w->dw, a);
     else
-        SSE_LAUNCH_KERNEL(k_walkers<false>, grid, block, smem, w->stream, m->dm, w->dw, a);
+        SSE_LAUNCH_KERNEL(k_phase<false>, grid, PHASE_WARPS * 32, smem, w->stream, m->dm, w->dw, a);
     CU(cudaGetLastError());
+    return 0;
+}
+
+// Launch shape of k_sweep: one CTA per SM (fewer if there are fewer walkers); worm warps so that every walker of a CTA
+// has its own lane (up to 8 warps = 256 chains per SM: more does not raise the random-sector rate of the memory system,
+// profiles/r2_chase_lanes.txt), the remaining warps stream.
+struct SweepShape {
+    int grid, worm_warps, stream_warps, level, nloc_max;
+    size_t smem;
+};
+
+int32_t sweep_shape(const sse_walkers *w, SweepShape &sh) {
+    const sse_model *m = w->model;
+    const int W = w->dw.W, N = m->dm.n_sites;
+    sh.grid = std::min(W, m->n_sm);
+    sh.nloc_max = (W + sh.grid - 1) / sh.grid;
+    int ww = w->worm_warps > 0 ? w->worm_warps : std::min(8, (sh.nloc_max + 31) / 32);
+    int sw = w->stream_warps > 0 ? w->stream_warps : std::min(SWEEP_MAX_WARPS - ww, std::max(1, std::min(16, sh.nloc_max)));
+    if (ww < 1 || sw < 1 || ww + sw > SWEEP_MAX_WARPS) return fail("launch shape: need 1 <= worm_warps, 1 <= stream_warps, worm_warps + stream_warps <= 24");
+    const int budget = 227 * 1024 - 1024;
+    const int fixed = m->dm.tl.bytes + sched_bytes(sh.nloc_max);
+    sh.level = 1;
+    if (const char *lv = getenv("SSE_B200_SMEM_LEVEL")) sh.level = std::min(sh.level, std::max(0, atoi(lv)));
+    if (sh.level == 1) {
+        // as many streaming warps with state[] and mark[] in shared memory as fit; below 4, keep them in global memory instead
+        const int per = stream_scratch_bytes(N, 1);
+        const int fit = (budget - fixed) / per;
+        if (fit >= std::min(sw, 4)) sw = std::min(sw, fit);
+        else sh.level = 0;
+    }
+    if (!sh.level && !w->dw.mark) return fail("internal: mark[] scratch missing");
+    sh.worm_warps = ww;
+    sh.stream_warps = sw;
+    sh.smem = (size_t)fixed + (size_t)sw * stream_scratch_bytes(N, sh.level);
+    if ((int)sh.smem > budget) return fail("launch shape: shared memory exceeded (too many walkers per SM for the status table)");
+    return 0;
+}
+
+int32_t launch_sweep(sse_walkers *w, int n_sweeps, unsigned long long budget, int reset, int thermalized, int measure) {
+    const sse_model *m = w->model;
+    CU(cudaSetDevice(m->device));
+    SweepShape sh;
+    if (int32_t s = sweep_shape(w, sh)) return s;
+    SweepArgs a{};
+    a.n_sweeps = n_sweeps;
+    a.budget = budget;
+    a.reset = reset;
+    a.thermalized = thermalized;
+    a.measure = measure;
+    a.worm_warps = sh.worm_warps;
+    a.stream_warps = sh.stream_warps;
+    a.level = sh.level;
+    a.nloc_max = sh.nloc_max;
+    const int block = (sh.worm_warps + sh.stream_warps) * 32;
+    if (sh.smem > 48 * 1024) {
+        CU(cudaFuncSetAttribute(k_sweep<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh.smem));
+        CU(cudaFuncSetAttribute(k_sweep<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh.smem));
+    }
+    if (w->dw.inj)
+        SSE_LAUNCH_KERNEL(k_sweep<true>, sh.grid, block, sh.smem, w->stream, m->dm, w->dw, a);
+    else
+        SSE_LAUNCH_KERNEL(k_sweep<false>, sh.grid, block, sh.smem, w->stream, m->dm, w->dw, a);
+    CU(cudaGetLastError());
+    w->have_vl = false;
     return 0;
 }
 
@@ -176,15 +215,19 @@ int32_t dev_alloc(sse_walkers *w, T **p, size_t count, bool zero) {
     return 0;
 }
 
-int32_t ensure_committed(sse_walkers *w) {
-    if (w->indexed) {
-        LaunchArgs a{};
-        a.mode = MODE_COMMIT;
-        if (int32_t s = launch(w, a)) return s;
-        w->indexed = false;
-    }
+// sse_get_state, sse_measure, sse_double_beta and the parity hooks need every walker between two sweeps
+int32_t require_between_sweeps(sse_walkers *w, const char *who) {
+    CU(cudaStreamSynchronize(w->stream));
+    if (!w->maybe_in_flight) return 0;
+    std::vector<uint32_t> ph;
+    if (int32_t s = get_field(w, CTL_OFF(phase), ph)) return s;
+    for (int i = 0; i < w->dw.W; ++i)
+        if (ph[i]) return fail(std::string(who) + ": walker " + std::to_string(i) + " is parked inside a sweep (sse_advance); call sse_finish_sweeps first");
+    w->maybe_in_flight = false;
     return 0;
 }
+
+int64_t ring_size(int64_t n_cap) { return n_cap + std::max<int64_t>(2048, n_cap / 16); }
 
 }  // namespace
 
@@ -206,6 +249,8 @@ int32_t sse_model_create(const sse_model_desc *d, sse_model **out) {
     std::unique_ptr<sse_model, int32_t (*)(sse_model *)> guard(new sse_model(), sse_model_destroy);  // freed on every error path
     sse_model *m = guard.get();
     CU(cudaGetDevice(&m->device));
+    CU(cudaDeviceGetAttribute(&m->n_sm, cudaDevAttrMultiProcessorCount, m->device));
+    if (const char *e = getenv("SSE_B200_CTAS")) m->n_sm = std::max(1, atoi(e));  // tests: force a grid size
     m->n_types = d->n_types;
     m->bond_type.assign(d->bond_type, d->bond_type + d->n_bonds);
     m->bond_sites.assign(d->bond_sites, d->bond_sites + 2 * d->n_bonds);
@@ -302,26 +347,6 @@ int32_t sse_model_create(const sse_model_desc *d, sse_model **out) {
         if (o < 0) { t1[i] = make_uint4(0u, 0x7ff00000u, 0u, 0u); continue; }
         t1[i] = make_uint4(outc[o].x, outc[o].y, outc[o].z, outc[o].w | ((uint32_t)(o + 1) << 6) | (uint32_t)(c - 1));
     }
-    // most likely exit leg per entrance leg, marginalised over vertices (weighted by their weight) and worms
-    uint32_t pred_exit = 0;
-    for (int leg = 0; leg < 4; ++leg) {
-        double score[4] = {0, 0, 0, 0};
-        for (int v = 0; v < nv; ++v)
-            for (int wm = 0; wm < d->max_worm; ++wm) {
-                int i = (v * d->max_worm + wm) * 4 + leg;
-                int o = d->trans_offset[i], c = d->trans_count[i];
-                if (o < 0) continue;
-                double prev = 0;
-                for (int j = 0; j < c; ++j) {
-                    score[d->out_leg[o + j]] += d->weights[v] * (d->out_cumprob[o + j] - prev);
-                    prev = d->out_cumprob[o + j];
-                }
-            }
-        int best = 0;
-        for (int j = 1; j < 4; ++j)
-            if (score[j] > score[best]) best = j;
-        pred_exit |= (uint32_t)best << (2 * leg);
-    }
     CU(upload(&m->d_bond_info, bi));
     CU(upload(&m->d_site_dim, m->site_dim));
     CU(upload(&m->d_blob, blob));
@@ -341,8 +366,6 @@ int32_t sse_model_create(const sse_model_desc *d, sse_model **out) {
     dm.site_dim = m->d_site_dim;
     dm.est_values = m->d_est;
     dm.tab_blob = m->d_blob;
-    dm.pred_exit = pred_exit;
-    dm.variant = getenv("SSE_B200_VARIANT") ? (uint32_t)atoi(getenv("SSE_B200_VARIANT")) : 0u;
     dm.tl = tl;
     *out = guard.release();
     return 0;
@@ -358,11 +381,12 @@ int32_t sse_model_destroy(sse_model *m) {
     return 0;
 }
 
+
 int32_t sse_walkers_create(const sse_model *m, const sse_walkers_opts *o, sse_walkers **out) {
     if (!m || !o || !out) return fail("sse_walkers_create: null argument");
     if (o->n_walkers <= 0) return fail("sse_walkers_create: n_walkers must be positive");
     if (o->m_capacity < 128 || o->m_capacity >= (1ll << 31)) return fail("sse_walkers_create: m_capacity out of range [128, 2^31)");
-    if (o->n_capacity < 64 || o->n_capacity > (1ll << 22)) return fail("sse_walkers_create: n_capacity out of range [64, 2^22]");
+    if (o->n_capacity < 64 || o->n_capacity > (1ll << 22) - 1) return fail("sse_walkers_create: n_capacity out of range [64, 2^22 - 1]");
     if (o->device >= 0 && o->device != m->device) return fail("sse_walkers_create: model was created on another device");
     CU(cudaSetDevice(m->device));
     std::unique_ptr<sse_walkers, int32_t (*)(sse_walkers *)> guard(new sse_walkers(), sse_walkers_destroy);  // freed on every error path
@@ -372,34 +396,26 @@ int32_t sse_walkers_create(const sse_model *m, const sse_walkers_opts *o, sse_wa
     const int W = o->n_walkers, N = m->dm.n_sites;
     dw.W = W;
     dw.M_cap = (o->m_capacity + 31) & ~31ll;
+    dw.Mw_cap = dw.M_cap / 32;
     dw.n_cap = o->n_capacity;
+    dw.R_cap = ring_size(dw.n_cap);
     dw.n_obs = SSE_OBS_FIXED + SSE_OBS_PER_ESTIMATOR * m->dm.n_est;
     int32_t s = 0;
-    s |= dev_alloc(w, &dw.ops, (size_t)W * dw.M_cap, true);
-    s |= dev_alloc(w, &dw.rec, 2 * (size_t)W * dw.n_cap, false);  // 32-byte records
+    s |= dev_alloc(w, &dw.words, (size_t)W * dw.Mw_cap, true);
+    s |= dev_alloc(w, &dw.rec, (size_t)W * dw.R_cap, false);
     s |= dev_alloc(w, &dw.state, (size_t)W * N, false);
-    // per-warp state[N] + mark[N] live in shared memory when 7 CTAs/SM still fit, else in global scratch
-    // level 2 (+ vlast) only while 7 CTAs/SM still fit (32 KB per CTA); level 1 up to 99 KB per CTA
-    dw.smem_state = 0;
-    if (m->dm.tl.bytes + WARPS_PER_CTA * warp_scratch_bytes(N, 1) <= 99 * 1024) dw.smem_state = 1;
-    if (m->dm.tl.bytes + WARPS_PER_CTA * warp_scratch_bytes(N, 2) <= 32 * 1024) dw.smem_state = 2;
-    if (const char *lv = getenv("SSE_B200_SMEM_LEVEL")) dw.smem_state = std::min(dw.smem_state, std::max(0, atoi(lv)));  // tests: force the large-lattice paths
-    // global mark[] scratch: needed by whichever kernel (one walker per warp, or 2/4 per warp) runs at level 0
-    if (!dw.smem_state || !multi_level(m, 2, 7) || !multi_level(m, 4, 5) || getenv("SSE_B200_SMEM_LEVEL"))
-        s |= dev_alloc(w, &dw.mark, (size_t)W * N, true);
+    // stream warps keep state[N] + mark[N] in shared memory when they fit, else in global scratch
+    {
+        const int fixed = m->dm.tl.bytes + sched_bytes(1024);
+        const bool fits_sweep = (227 * 1024 - 1024 - fixed) / stream_scratch_bytes(N, 1) >= 4;
+        if (!fits_sweep || !phase_level(m) || getenv("SSE_B200_SMEM_LEVEL")) s |= dev_alloc(w, &dw.mark, (size_t)W * N, true);
+    }
     s |= dev_alloc(w, &dw.vfirst, (size_t)W * N, false);
     s |= dev_alloc(w, &dw.vlast, (size_t)W * N, false);
-    s |= dev_alloc(w, &dw.T, W, true);
-    s |= dev_alloc(w, &dw.M, W, true);
-    s |= dev_alloc(w, &dw.n, W, true);
-    s |= dev_alloc(w, &dw.num_worms, W, true);
-    s |= dev_alloc(w, &dw.avg_wl, W, true);
-    s |= dev_alloc(w, &dw.last_wlf, W, true);
-    s |= dev_alloc(w, &dw.draws, W, true);
-    s |= dev_alloc(w, &dw.flags, W, true);
+    s |= dev_alloc(w, &dw.ctl, (size_t)W, true);
     s |= dev_alloc(w, &dw.acc, (size_t)W * dw.n_obs, true);
     s |= dev_alloc(w, &dw.acc_cnt, (size_t)W * 2, true);
-    s |= dev_alloc(w, &dw.counters, 8, true);
+    s |= dev_alloc(w, &dw.counters, SSE_N_COUNTERS, true);
     s |= dev_alloc(w, &dw.dbg_len, W, true);
     s |= dev_alloc(w, &dw.obs_out, (size_t)W * dw.n_obs, true);
     if (s) return 1;
@@ -409,28 +425,41 @@ int32_t sse_walkers_create(const sse_model *m, const sse_walkers_opts *o, sse_wa
     dw.wid_off = o->walker_id_offset;
     dw.twlf = o->target_worm_length_fraction;
     dw.atten = o->num_worms_attenuation_factor;
-    std::vector<double> T(o->T, o->T + W), nw(W, o->init_num_worms), awl(W, 1.0), wlf(W, NAN);
-    for (double t : T)
-        if (!(t > 0)) return fail("sse_walkers_create: temperatures must be positive");
-    CU(cudaMemcpy(dw.T, T.data(), sizeof(double) * W, cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(dw.num_worms, nw.data(), sizeof(double) * W, cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(dw.avg_wl, awl.data(), sizeof(double) * W, cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(dw.last_wlf, wlf.data(), sizeof(double) * W, cudaMemcpyHostToDevice));
+    std::vector<WalkerCtl> ctl(W);
+    for (int i = 0; i < W; ++i) {
+        if (!(o->T[i] > 0)) return fail("sse_walkers_create: temperatures must be positive");
+        memset(&ctl[i], 0, sizeof(WalkerCtl));
+        ctl[i].T = o->T[i];
+        ctl[i].num_worms = o->init_num_worms;
+        ctl[i].avg_wl = 1.0;
+        ctl[i].last_wlf = NAN;
+    }
+    CU(cudaMemcpy(dw.ctl, ctl.data(), sizeof(WalkerCtl) * W, cudaMemcpyHostToDevice));
     CU(cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking));
     w->own_stream = true;
-    if (const char *ch = getenv("SSE_B200_CHAINS")) {
-        if (sse_set_walkers_per_warp(w, atoi(ch))) return 1;
+    if (const char *e = getenv("SSE_B200_WORM_WARPS")) w->worm_warps = atoi(e);
+    if (const char *e = getenv("SSE_B200_STREAM_WARPS")) w->stream_warps = atoi(e);
+    {
+        SweepShape sh;
+        if (sweep_shape(w, sh)) return 1;
     }
     *out = guard.release();
     return 0;
 }
 
-int32_t sse_set_walkers_per_warp(sse_walkers *w, int32_t walkers_per_warp) {
+int32_t sse_set_launch_shape(sse_walkers *w, int32_t worm_warps, int32_t stream_warps) {
     if (!w) return fail("null handle");
-    if (walkers_per_warp != 1 && walkers_per_warp != 2 && walkers_per_warp != 4)
-        return fail("sse_set_walkers_per_warp: supported values are 1, 2 and 4");
+    if (worm_warps < 0 || stream_warps < 0) return fail("sse_set_launch_shape: negative warp count");
     CU(cudaStreamSynchronize(w->stream));
-    w->chains = walkers_per_warp;
+    const int ow = w->worm_warps, os = w->stream_warps;
+    w->worm_warps = worm_warps;
+    w->stream_warps = stream_warps;
+    SweepShape sh;
+    if (sweep_shape(w, sh)) {
+        w->worm_warps = ow;
+        w->stream_warps = os;
+        return 1;
+    }
     return 0;
 }
 
@@ -460,38 +489,71 @@ int32_t sse_init(sse_walkers *w, int64_t init_opstring_cutoff, int32_t diagonal_
     if (!w) return fail("null handle");
     const int W = w->dw.W;
     CU(cudaSetDevice(w->model->device));
-    std::vector<double> T(W);
-    CU(cudaMemcpy(T.data(), w->dw.T, sizeof(double) * W, cudaMemcpyDeviceToHost));
-    std::vector<int> M(W), n(W, 0);
+    CU(cudaStreamSynchronize(w->stream));
+    std::vector<WalkerCtl> ctl(W);
+    CU(cudaMemcpyAsync(ctl.data(), w->dw.ctl, sizeof(WalkerCtl) * W, cudaMemcpyDeviceToHost, w->stream));
+    CU(cudaStreamSynchronize(w->stream));
     for (int i = 0; i < W; ++i) {
         // round(Int, length(sites) * T) (src/sse.jl:51): round-half-even
-        long long m0 = init_opstring_cutoff >= 0 ? init_opstring_cutoff : (long long)std::nearbyint((double)w->model->dm.n_sites * T[i]);
+        long long m0 = init_opstring_cutoff >= 0 ? init_opstring_cutoff : (long long)std::nearbyint((double)w->model->dm.n_sites * ctl[i].T);
         if (m0 > w->dw.M_cap) return fail("sse_init: init_opstring_cutoff exceeds m_capacity");
-        M[i] = (int)m0;
+        WalkerCtl &c = ctl[i];
+        c.M = (int)m0;
+        c.n = 0;
+        c.G = 0;
+        c.flags = 0;  // a walker that overflowed earlier starts afresh
+        c.phase = 0;
+        c.worms_left = 0;
+        c.inworm = 0;
+        c.sweep_visits = 0;
+        c.sweeps_done = 0;
+        c.sweeps_left = 0;
     }
-    CU(cudaMemsetAsync(w->dw.ops, 0, sizeof(uint32_t) * (size_t)W * w->dw.M_cap, w->stream));
-    CU(cudaMemcpyAsync(w->dw.M, M.data(), sizeof(int) * W, cudaMemcpyHostToDevice, w->stream));
-    CU(cudaMemcpyAsync(w->dw.n, n.data(), sizeof(int) * W, cudaMemcpyHostToDevice, w->stream));
-    w->indexed = false;
+    CU(cudaMemsetAsync(w->dw.words, 0, sizeof(uint2) * (size_t)W * w->dw.Mw_cap, w->stream));
+    CU(cudaMemcpyAsync(w->dw.ctl, ctl.data(), sizeof(WalkerCtl) * W, cudaMemcpyHostToDevice, w->stream));
+    CU(cudaMemsetAsync(w->dw.counters + SSE_CNT_ANY_FATAL, 0, sizeof(unsigned long long), w->stream));
+    CU(cudaStreamSynchronize(w->stream));  // ctl is a host vector: the copy must be done before it goes out of scope
     w->have_vl = false;
-    LaunchArgs a{};
+    w->maybe_in_flight = false;
+    PhaseArgs a{};
     a.mode = MODE_INIT;
     a.warmup = diagonal_warmup_sweeps;
-    if (int32_t s = launch(w, a)) return s;
-    return check_flags(w);
+    if (int32_t s = launch_phase(w, a)) return s;
+    return sse_sync(w);
 }
 
 int32_t sse_sweep(sse_walkers *w, int32_t n_sweeps, int32_t thermalized, int32_t measure) {
     if (!w) return fail("null handle");
     if (n_sweeps <= 0) return 0;
-    if (int32_t s = ensure_committed(w)) return s;
-    LaunchArgs a{};
-    a.mode = MODE_SWEEP;
-    a.n_sweeps = n_sweeps;
-    a.thermalized = thermalized;
-    a.measure = measure;
-    w->have_vl = false;
-    return launch(w, a);
+    return launch_sweep(w, n_sweeps, ~0ull, 1, thermalized, measure);
+}
+
+int32_t sse_advance(sse_walkers *w, int32_t max_sweeps, uint64_t visit_budget, int32_t thermalized, int32_t measure) {
+    if (!w) return fail("null handle");
+    if (max_sweeps <= 0 || visit_budget == 0) return 0;
+    w->maybe_in_flight = true;
+    return launch_sweep(w, max_sweeps, (unsigned long long)visit_budget, 1, thermalized, measure);
+}
+
+int32_t sse_finish_sweeps(sse_walkers *w, int32_t thermalized, int32_t measure) {
+    if (!w) return fail("null handle");
+    // quota 0: sweeps in flight are completed (their worm phase runs to its end), no new sweep starts
+    if (int32_t s = launch_sweep(w, 0, ~0ull, 1, thermalized, measure)) return s;
+    w->maybe_in_flight = false;
+    return 0;
+}
+
+int32_t sse_get_progress(sse_walkers *w, uint64_t *sweeps_done, uint8_t *in_flight) {
+    if (!w || !sweeps_done) return fail("null argument");
+    std::vector<unsigned long long> sd;
+    if (int32_t s = get_field(w, CTL_OFF(sweeps_done), sd)) return s;
+    for (int i = 0; i < w->dw.W; ++i) sweeps_done[i] = sd[i];
+    if (in_flight) {
+        std::vector<uint32_t> ph;
+        if (int32_t s = get_field(w, CTL_OFF(phase), ph)) return s;
+        for (int i = 0; i < w->dw.W; ++i) in_flight[i] = (uint8_t)(ph[i] != 0);
+    }
+    return 0;
 }
 
 int32_t sse_sync(sse_walkers *w) {
@@ -502,11 +564,10 @@ int32_t sse_sync(sse_walkers *w) {
 
 int32_t sse_measure(sse_walkers *w, double *out) {
     if (!w || !out) return fail("null argument");
-    LaunchArgs a{};
+    if (int32_t s = require_between_sweeps(w, "sse_measure")) return s;
+    PhaseArgs a{};
     a.mode = MODE_MEASURE;
-    a.indexed = w->indexed;
-    if (int32_t s = launch(w, a)) return s;
-    w->indexed = false;  // MODE_MEASURE commits
+    if (int32_t s = launch_phase(w, a)) return s;
     CU(cudaMemcpyAsync(out, w->dw.obs_out, sizeof(double) * (size_t)w->dw.W * w->dw.n_obs, cudaMemcpyDeviceToHost, w->stream));
     CU(cudaStreamSynchronize(w->stream));
     return check_flags(w);
@@ -532,58 +593,85 @@ int32_t sse_accumulators_device_ptr(sse_walkers *w, void **sums, void **counts) 
     return 0;
 }
 
-int32_t sse_fetch_counters(sse_walkers *w, uint64_t out[8], int32_t reset) {
+int32_t sse_fetch_counters(sse_walkers *w, uint64_t out[SSE_N_COUNTERS], int32_t reset) {
     if (!w || !out) return fail("null argument");
-    CU(cudaMemcpyAsync(out, w->dw.counters, 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost, w->stream));
-    if (reset) CU(cudaMemsetAsync(w->dw.counters, 0, 8 * sizeof(uint64_t), w->stream));
+    CU(cudaMemcpyAsync(out, w->dw.counters, SSE_N_COUNTERS * sizeof(uint64_t), cudaMemcpyDeviceToHost, w->stream));
+    if (reset) CU(cudaMemsetAsync(w->dw.counters, 0, SSE_CNT_ANY_FATAL * sizeof(uint64_t), w->stream));  // the fatal marker stays
     CU(cudaStreamSynchronize(w->stream));
     return 0;
 }
 
+namespace {
+
+// device op code -> reference OperCode (opercode.jl:43-47)
+inline uint64_t to_opercode(const sse_model *m, uint32_t op) {
+    const uint32_t bond = op_bond(op), gv = op_gv(op);
+    const uint64_t lv = (uint64_t)(gv - m->type_vertex_off[m->bond_type[bond]] + 1);
+    const uint64_t vcode = ((op >> 1) & 1u) | (lv << 1);  // VertexCode(diagonal, idx) (opercode.jl:18-21)
+    return 1ull | (vcode << 1) | ((uint64_t)(bond + 1) << 26);
+}
+
+// Download walker i's string: bits/ranks of its M slots and its n records (unrolled from the ring).
+int32_t download_string(sse_walkers *w, int i, const WalkerCtl &c, std::vector<uint2> &words, std::vector<uint4> &rec) {
+    const int nw = (c.M + 31) / 32;
+    words.resize(nw);
+    rec.resize(c.n);
+    if (nw) CU(cudaMemcpyAsync(words.data(), w->dw.words + (size_t)i * w->dw.Mw_cap, sizeof(uint2) * nw, cudaMemcpyDeviceToHost, w->stream));
+    const uint4 *ring0 = w->dw.rec + (size_t)i * w->dw.R_cap;
+    const int64_t first = std::min<int64_t>(c.n, w->dw.R_cap - c.G);
+    if (first > 0) CU(cudaMemcpyAsync(rec.data(), ring0 + c.G, sizeof(uint4) * first, cudaMemcpyDeviceToHost, w->stream));
+    if (c.n > first) CU(cudaMemcpyAsync(rec.data() + first, ring0, sizeof(uint4) * (c.n - first), cudaMemcpyDeviceToHost, w->stream));
+    CU(cudaStreamSynchronize(w->stream));
+    return 0;
+}
+
+}  // namespace
+
 int32_t sse_get_state(sse_walkers *w, int32_t i, sse_walker_state *st) {
     if (!w || !st) return fail("null argument");
     if (i < 0 || i >= w->dw.W) return fail("sse_get_state: walker index out of range");
-    if (int32_t s = ensure_committed(w)) return s;
+    if (int32_t s = require_between_sweeps(w, "sse_get_state")) return s;
     const sse_model *m = w->model;
-    int M = 0, n = 0;
-    unsigned long long draws = 0;
+    WalkerCtl c;
+    CU(cudaMemcpyAsync(&c, w->dw.ctl + i, sizeof(c), cudaMemcpyDeviceToHost, w->stream));
     CU(cudaStreamSynchronize(w->stream));
-    CU(cudaMemcpy(&M, w->dw.M + i, sizeof(int), cudaMemcpyDeviceToHost));
-    CU(cudaMemcpy(&n, w->dw.n + i, sizeof(int), cudaMemcpyDeviceToHost));
-    CU(cudaMemcpy(&draws, w->dw.draws + i, sizeof(draws), cudaMemcpyDeviceToHost));
-    CU(cudaMemcpy(&st->avg_worm_length, w->dw.avg_wl + i, sizeof(double), cudaMemcpyDeviceToHost));
-    CU(cudaMemcpy(&st->num_worms, w->dw.num_worms + i, sizeof(double), cudaMemcpyDeviceToHost));
-    CU(cudaMemcpy(&st->T, w->dw.T + i, sizeof(double), cudaMemcpyDeviceToHost));
-    st->num_operators = n;
-    st->rng_draws = draws;
+    st->num_operators = c.n;
+    st->rng_draws = c.draws;
+    st->avg_worm_length = c.avg_wl;
+    st->num_worms = c.num_worms;
+    st->T = c.T;
     if (st->operators) {
-        if (st->operators_len < M) { st->operators_len = M; return fail("sse_get_state: operators buffer too small"); }
-        std::vector<uint32_t> ops(M);
-        if (M) CU(cudaMemcpy(ops.data(), w->dw.ops + (size_t)i * w->dw.M_cap, sizeof(uint32_t) * M, cudaMemcpyDeviceToHost));
-        for (int p = 0; p < M; ++p) {
-            uint32_t op = ops[p];
-            if (!op) { st->operators[p] = 0; continue; }
-            uint32_t bond = op_bond(op), gv = op_gv(op);
-            uint64_t lv = (uint64_t)(gv - m->type_vertex_off[m->bond_type[bond]] + 1);
-            uint64_t vcode = ((op >> 1) & 1u) | (lv << 1);                // VertexCode(diagonal, idx) (opercode.jl:18-21)
-            st->operators[p] = 1ull | (vcode << 1) | ((uint64_t)(bond + 1) << 26);  // OperCode(bond, vertex) (opercode.jl:43-47)
+        if (st->operators_len < c.M) { st->operators_len = c.M; return fail("sse_get_state: operators buffer too small"); }
+        std::vector<uint2> words;
+        std::vector<uint4> rec;
+        if (int32_t s = download_string(w, i, c, words, rec)) return s;
+        int64_t k = 0;
+        for (int p = 0; p < c.M; ++p) {
+            if (!((words[p >> 5].x >> (p & 31)) & 1u)) { st->operators[p] = 0; continue; }
+            if (k >= c.n) return fail("sse_get_state: corrupt occupancy bitmap");
+            st->operators[p] = to_opercode(m, rec[k++].x);
         }
+        if (k != c.n) return fail("sse_get_state: occupancy bitmap and operator count disagree");
     }
-    st->operators_len = M;
-    if (st->state) CU(cudaMemcpy(st->state, w->dw.state + (size_t)i * m->dm.n_sites, m->dm.n_sites, cudaMemcpyDeviceToHost));
+    st->operators_len = c.M;
+    if (st->state) {
+        CU(cudaMemcpyAsync(st->state, w->dw.state + (size_t)i * m->dm.n_sites, m->dm.n_sites, cudaMemcpyDeviceToHost, w->stream));
+        CU(cudaStreamSynchronize(w->stream));
+    }
     return 0;
 }
 
 int32_t sse_set_state(sse_walkers *w, int32_t i, const sse_walker_state *st) {
     if (!w || !st || !st->operators || !st->state) return fail("null argument");
     if (i < 0 || i >= w->dw.W) return fail("sse_set_state: walker index out of range");
-    if (int32_t s = ensure_committed(w)) return s;
     const sse_model *m = w->model;
     const long long M = st->operators_len;
     if (M < 0 || M > w->dw.M_cap) return fail("sse_set_state: operator string longer than m_capacity");
-    std::vector<uint32_t> ops((size_t)w->dw.M_cap, 0u);
+    std::vector<uint2> words((size_t)w->dw.Mw_cap, make_uint2(0u, 0u));
+    std::vector<uint4> rec;
     long long n = 0;
     for (long long p = 0; p < M; ++p) {
+        if ((p & 31) == 0) words[p >> 5].y = (uint32_t)n;
         uint64_t code = st->operators[p];
         if (code == 0) continue;
         long long bond = (long long)(code >> 26) - 1;
@@ -594,54 +682,56 @@ int32_t sse_set_state(sse_walkers *w, int32_t i, const sse_walker_state *st) {
         long long gv = m->type_vertex_off[t] + lv - 1;
         if (lv < 1 || gv >= m->type_vertex_off[t + 1]) return fail("sse_set_state: vertex index out of range at slot " + std::to_string(p));
         if ((uint32_t)(vcode & 1) != m->is_diag[gv]) return fail("sse_set_state: diagonal flag inconsistent with the vertex table at slot " + std::to_string(p));
-        ops[p] = op_pack((uint32_t)bond, (uint32_t)gv, (uint32_t)(vcode & 1));
+        words[p >> 5].x |= 1u << (p & 31);
+        rec.push_back(make_uint4(op_pack((uint32_t)bond, (uint32_t)gv, (uint32_t)(vcode & 1)), 0u, 0u, 0u));
         ++n;
     }
     if (n != st->num_operators) return fail("sse_set_state: num_operators does not match the operator string");
+    if (n > w->dw.n_cap) return fail("sse_set_state: more operators than n_capacity");
     for (int s = 0; s < m->dm.n_sites; ++s)
         if (st->state[s] < 1 || st->state[s] > m->site_dim[s]) return fail("sse_set_state: state index out of range at site " + std::to_string(s));
     CU(cudaStreamSynchronize(w->stream));
-    int Mi = (int)M, ni = (int)n;
-    unsigned long long draws = st->rng_draws;
-    uint32_t zero = 0;
-    CU(cudaMemcpy(w->dw.ops + (size_t)i * w->dw.M_cap, ops.data(), sizeof(uint32_t) * ops.size(), cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(w->dw.state + (size_t)i * m->dm.n_sites, st->state, m->dm.n_sites, cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(w->dw.M + i, &Mi, sizeof(int), cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(w->dw.n + i, &ni, sizeof(int), cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(w->dw.draws + i, &draws, sizeof(draws), cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(w->dw.avg_wl + i, &st->avg_worm_length, sizeof(double), cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(w->dw.num_worms + i, &st->num_worms, sizeof(double), cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(w->dw.T + i, &st->T, sizeof(double), cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(w->dw.flags + i, &zero, sizeof(uint32_t), cudaMemcpyHostToDevice));
+    WalkerCtl c;
+    memset(&c, 0, sizeof(c));
+    c.T = st->T;
+    c.num_worms = st->num_worms;
+    c.avg_wl = st->avg_worm_length;
+    c.last_wlf = NAN;
+    c.draws = st->rng_draws;
+    c.M = (int)M;
+    c.n = (int)n;
+    CU(cudaMemcpyAsync(w->dw.words + (size_t)i * w->dw.Mw_cap, words.data(), sizeof(uint2) * words.size(), cudaMemcpyHostToDevice, w->stream));
+    if (n) CU(cudaMemcpyAsync(w->dw.rec + (size_t)i * w->dw.R_cap, rec.data(), sizeof(uint4) * rec.size(), cudaMemcpyHostToDevice, w->stream));
+    CU(cudaMemcpyAsync(w->dw.state + (size_t)i * m->dm.n_sites, st->state, m->dm.n_sites, cudaMemcpyHostToDevice, w->stream));
+    CU(cudaMemcpyAsync(w->dw.ctl + i, &c, sizeof(c), cudaMemcpyHostToDevice, w->stream));
+    CU(cudaStreamSynchronize(w->stream));  // the staging vectors above are about to be freed
     w->have_vl = false;
     return 0;
 }
 
 int32_t sse_get_flags(sse_walkers *w, uint32_t *flags) {
     if (!w || !flags) return fail("null argument");
-    CU(cudaStreamSynchronize(w->stream));
-    CU(cudaMemcpy(flags, w->dw.flags, sizeof(uint32_t) * w->dw.W, cudaMemcpyDeviceToHost));
+    std::vector<uint32_t> f;
+    if (int32_t s = get_field(w, CTL_OFF(flags), f)) return s;
+    std::copy(f.begin(), f.end(), flags);
     return 0;
 }
 
 int32_t sse_get_num_operators(sse_walkers *w, int64_t *out) {
     if (!w || !out) return fail("null argument");
-    std::vector<int> n(w->dw.W);
-    CU(cudaStreamSynchronize(w->stream));
-    CU(cudaMemcpy(n.data(), w->dw.n, sizeof(int) * n.size(), cudaMemcpyDeviceToHost));
+    std::vector<int> n;
+    if (int32_t s = get_field(w, CTL_OFF(n), n)) return s;
     for (size_t i = 0; i < n.size(); ++i) out[i] = n[i];
     return 0;
 }
 
 int32_t sse_pt_log_weight_ratio(sse_walkers *w, const double *new_T, double *out) {
     if (!w || !new_T || !out) return fail("null argument");
-    const int W = w->dw.W;
-    std::vector<int> n(W);
-    std::vector<double> T(W);
-    CU(cudaStreamSynchronize(w->stream));
-    CU(cudaMemcpy(n.data(), w->dw.n, sizeof(int) * W, cudaMemcpyDeviceToHost));
-    CU(cudaMemcpy(T.data(), w->dw.T, sizeof(double) * W, cudaMemcpyDeviceToHost));
-    for (int i = 0; i < W; ++i) out[i] = -(double)n[i] * std::log(new_T[i] / T[i]);  // src/sse.jl:395
+    std::vector<int> n;
+    std::vector<double> T;
+    if (int32_t s = get_field(w, CTL_OFF(n), n)) return s;
+    if (int32_t s = get_field(w, CTL_OFF(T), T)) return s;
+    for (int i = 0; i < w->dw.W; ++i) out[i] = -(double)n[i] * std::log(new_T[i] / T[i]);  // src/sse.jl:395
     return 0;
 }
 
@@ -649,9 +739,7 @@ int32_t sse_set_temperature(sse_walkers *w, const double *T) {
     if (!w || !T) return fail("null argument");
     for (int i = 0; i < w->dw.W; ++i)
         if (!(T[i] > 0)) return fail("sse_set_temperature: temperatures must be positive");
-    CU(cudaMemcpyAsync(w->dw.T, T, sizeof(double) * w->dw.W, cudaMemcpyHostToDevice, w->stream));  // src/sse.jl:403
-    CU(cudaStreamSynchronize(w->stream));
-    return 0;
+    return set_field(w, CTL_OFF(T), T);  // src/sse.jl:403
 }
 
 int32_t sse_set_controller(sse_walkers *w, double target_worm_length_fraction, double num_worms_attenuation_factor) {
@@ -666,10 +754,10 @@ int32_t sse_set_controller(sse_walkers *w, double target_worm_length_fraction, d
 
 int32_t sse_double_beta(sse_walkers *w) {
     if (!w) return fail("null handle");
-    if (int32_t s = ensure_committed(w)) return s;
+    if (int32_t s = require_between_sweeps(w, "sse_double_beta")) return s;
     CU(cudaSetDevice(w->model->device));
-    const int grid = (w->dw.W + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
-    SSE_LAUNCH_KERNEL(k_double_beta, grid, WARPS_PER_CTA * 32, 0, w->stream, w->dw);
+    const int grid = (w->dw.W + PHASE_WARPS - 1) / PHASE_WARPS;
+    SSE_LAUNCH_KERNEL(k_double_beta, grid, PHASE_WARPS * 32, 0, w->stream, w->dw);
     CU(cudaGetLastError());
     w->have_vl = false;
     return sse_sync(w);
@@ -684,68 +772,63 @@ int32_t sse_set_injected_stream(sse_walkers *w, const uint64_t *stream, int64_t 
     if (stream && len > 0) {
         size_t bytes = sizeof(uint64_t) * (size_t)len * w->dw.W;
         CU(cudaMalloc((void **)&w->d_inj, bytes));
-        CU(cudaMemcpy(w->d_inj, stream, bytes, cudaMemcpyHostToDevice));
+        CU(cudaMemcpyAsync(w->d_inj, stream, bytes, cudaMemcpyHostToDevice, w->stream));
         w->dw.inj = w->d_inj;
         w->dw.inj_len = len;
-        CU(cudaMemset(w->dw.draws, 0, sizeof(unsigned long long) * w->dw.W));
+        std::vector<unsigned long long> zero(w->dw.W, 0ull);
+        if (int32_t s = set_field(w, CTL_OFF(draws), zero.data())) return s;  // synchronises the stream
     }
-    return 0;
-}
-
-int32_t sse_dbg_set_variant(sse_model *m, uint32_t variant) {
-    if (!m) return fail("null handle");
-    m->dm.variant = variant;  // DevModel travels by value with every launch: takes effect at the next one
     return 0;
 }
 
 int32_t sse_dbg_diagonal_update(sse_walkers *w) {
     if (!w) return fail("null handle");
-    if (int32_t s = ensure_committed(w)) return s;
-    LaunchArgs a{};
+    if (int32_t s = require_between_sweeps(w, "sse_dbg_diagonal_update")) return s;
+    PhaseArgs a{};
     a.mode = MODE_DIAG;
     w->have_vl = false;
-    if (int32_t s = launch(w, a)) return s;
+    if (int32_t s = launch_phase(w, a)) return s;
     return sse_sync(w);
 }
 
 int32_t sse_dbg_make_vertex_list(sse_walkers *w) {
     if (!w) return fail("null handle");
-    if (int32_t s = ensure_committed(w)) return s;
-    LaunchArgs a{};
+    if (int32_t s = require_between_sweeps(w, "sse_dbg_make_vertex_list")) return s;
+    PhaseArgs a{};
     a.mode = MODE_MAKE_VL;
-    if (int32_t s = launch(w, a)) return s;
-    w->indexed = true;
+    if (int32_t s = launch_phase(w, a)) return s;
     w->have_vl = true;
     return sse_sync(w);
 }
 
 int32_t sse_dbg_worm_update(sse_walkers *w, int32_t thermalized) {
     if (!w) return fail("null handle");
-    if (!w->indexed || !w->have_vl) return fail("sse_dbg_worm_update: call sse_dbg_make_vertex_list first");
-    LaunchArgs a{};
+    if (!w->have_vl) return fail("sse_dbg_worm_update: call sse_dbg_make_vertex_list first");
+    PhaseArgs a{};
     a.mode = MODE_WORM_UPDATE;
     a.thermalized = thermalized;
-    if (int32_t s = launch(w, a)) return s;
+    if (int32_t s = launch_phase(w, a)) return s;
     return sse_sync(w);
 }
 
 int32_t sse_dbg_worm_traverse(sse_walkers *w, int32_t l0, int64_t p0, int32_t wormfunc0, int64_t *lengths) {
     if (!w || !lengths) return fail("null argument");
-    if (!w->indexed || !w->have_vl) return fail("sse_dbg_worm_traverse: call sse_dbg_make_vertex_list first");
+    if (!w->have_vl) return fail("sse_dbg_worm_traverse: call sse_dbg_make_vertex_list first");
     if (l0 < 1 || l0 > 4 || p0 < 1 || wormfunc0 < 1) return fail("sse_dbg_worm_traverse: start out of range");
-    std::vector<int> M(w->dw.W);
-    CU(cudaMemcpy(M.data(), w->dw.M, sizeof(int) * M.size(), cudaMemcpyDeviceToHost));
+    std::vector<int> M;
+    if (int32_t s = get_field(w, CTL_OFF(M), M)) return s;
     for (int m : M)
         if (p0 > m) return fail("sse_dbg_worm_traverse: p0 beyond the operator string");
-    LaunchArgs a{};
+    PhaseArgs a{};
     a.mode = MODE_WORM_TRAVERSE;
     a.l0 = l0 - 1;
     a.p0 = p0 - 1;
     a.w0 = wormfunc0;
-    if (int32_t s = launch(w, a)) return s;
+    if (int32_t s = launch_phase(w, a)) return s;
     if (int32_t s = sse_sync(w)) return s;
     std::vector<long long> len(w->dw.W);
-    CU(cudaMemcpy(len.data(), w->dw.dbg_len, sizeof(long long) * len.size(), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpyAsync(len.data(), w->dw.dbg_len, sizeof(long long) * len.size(), cudaMemcpyDeviceToHost, w->stream));
+    CU(cudaStreamSynchronize(w->stream));
     for (size_t i = 0; i < len.size(); ++i) lengths[i] = len[i];
     return 0;
 }
@@ -753,33 +836,46 @@ int32_t sse_dbg_worm_traverse(sse_walkers *w, int32_t l0, int64_t p0, int32_t wo
 int32_t sse_dbg_get_vertex_list(sse_walkers *w, int32_t i, int64_t *vertices, int64_t m_len, int64_t *v_first, int64_t *v_last) {
     if (!w || !vertices || !v_first || !v_last) return fail("null argument");
     if (i < 0 || i >= w->dw.W) return fail("walker index out of range");
-    if (!w->indexed || !w->have_vl) return fail("sse_dbg_get_vertex_list: no vertex list (call sse_dbg_make_vertex_list)");
+    if (!w->have_vl) return fail("sse_dbg_get_vertex_list: no vertex list (call sse_dbg_make_vertex_list)");
     CU(cudaStreamSynchronize(w->stream));
-    int M = 0, n = 0;
     const int N = w->model->dm.n_sites;
-    CU(cudaMemcpy(&M, w->dw.M + i, sizeof(int), cudaMemcpyDeviceToHost));
-    CU(cudaMemcpy(&n, w->dw.n + i, sizeof(int), cudaMemcpyDeviceToHost));
+    WalkerCtl c;
+    CU(cudaMemcpyAsync(&c, w->dw.ctl + i, sizeof(c), cudaMemcpyDeviceToHost, w->stream));
+    CU(cudaStreamSynchronize(w->stream));
+    const int M = c.M, n = c.n;
     if (m_len < M) return fail("sse_dbg_get_vertex_list: vertices buffer too small");
-    std::vector<uint32_t> ops(M), vf(N), vl(N);
-    std::vector<uint4> rec2(2 * (size_t)n), rec(n);
-    if (M) CU(cudaMemcpy(ops.data(), w->dw.ops + (size_t)i * w->dw.M_cap, sizeof(uint32_t) * M, cudaMemcpyDeviceToHost));
-    if (n) CU(cudaMemcpy(rec2.data(), w->dw.rec + 2 * (size_t)i * w->dw.n_cap, sizeof(uint4) * 2 * n, cudaMemcpyDeviceToHost));
-    for (int k = 0; k < n; ++k) rec[k] = rec2[2 * (size_t)k];
-    CU(cudaMemcpy(vf.data(), w->dw.vfirst + (size_t)i * N, sizeof(uint32_t) * N, cudaMemcpyDeviceToHost));
-    CU(cudaMemcpy(vl.data(), w->dw.vlast + (size_t)i * N, sizeof(uint32_t) * N, cudaMemcpyDeviceToHost));
-    std::vector<int64_t> pos(n, -1);
+    std::vector<uint2> words;
+    std::vector<uint4> rec;
+    if (int32_t s = download_string(w, i, c, words, rec)) return s;
+    std::vector<uint32_t> vf(N), vl(N);
+    CU(cudaMemcpyAsync(vf.data(), w->dw.vfirst + (size_t)i * N, sizeof(uint32_t) * N, cudaMemcpyDeviceToHost, w->stream));
+    CU(cudaMemcpyAsync(vl.data(), w->dw.vlast + (size_t)i * N, sizeof(uint32_t) * N, cudaMemcpyDeviceToHost, w->stream));
+    CU(cudaStreamSynchronize(w->stream));
+    std::vector<int64_t> pos(n, -1), rec_of(M, -1);
+    int64_t k = 0;
     for (int p = 0; p < M; ++p)
-        if (ops[p]) {
-            if (ops[p] - 1 >= (uint32_t)n) return fail("sse_dbg_get_vertex_list: corrupt record index");
-            pos[ops[p] - 1] = p;
+        if ((words[p >> 5].x >> (p & 31)) & 1u) {
+            if (k >= n) return fail("sse_dbg_get_vertex_list: corrupt occupancy bitmap");
+            if (words[p >> 5].y + (uint32_t)__builtin_popcount(words[p >> 5].x & ((1u << (p & 31)) - 1u)) != (uint32_t)k)
+                return fail("sse_dbg_get_vertex_list: corrupt rank");
+            pos[k] = p;
+            rec_of[p] = k++;
         }
-    auto link = [&](const uint4 &r, int j) -> uint32_t { return j == 0 ? r.x : j == 1 ? r.y : j == 2 ? r.z : r.w; };
+    auto link = [&](const uint4 &r, int j) -> uint32_t {
+        const uint64_t lo = (uint64_t)r.y | ((uint64_t)r.z << 32);
+        switch (j) {
+            case 0: return (uint32_t)(lo & NONE24);
+            case 1: return (uint32_t)((lo >> 24) & NONE24);
+            case 2: return (uint32_t)(((lo >> 48) | ((uint64_t)r.w << 16)) & NONE24);
+            default: return r.w >> 8;
+        }
+    };
     for (int64_t p = 0; p < M; ++p)
         for (int l = 0; l < 4; ++l) {
             int64_t *dst = vertices + (p * 4 + l) * 2;
             dst[0] = dst[1] = -1;
-            if (!ops[p]) continue;
-            uint32_t lk = link(rec[ops[p] - 1], l);
+            if (rec_of[p] < 0) continue;
+            uint32_t lk = link(rec[rec_of[p]], l);
             if (lk == NONE24 || (lk >> 2) >= (uint32_t)n) return fail("sse_dbg_get_vertex_list: dangling link");
             dst[0] = (lk & 3) + 1;
             dst[1] = pos[lk >> 2] + 1;
@@ -793,12 +889,6 @@ int32_t sse_dbg_get_vertex_list(sse_walkers *w, int32_t i, int64_t *vertices, in
         }
     }
     return 0;
-}
-
-int32_t sse_dbg_commit(sse_walkers *w) {
-    if (!w) return fail("null handle");
-    if (int32_t s = ensure_committed(w)) return s;
-    return sse_sync(w);
 }
 
 }  // extern "C"

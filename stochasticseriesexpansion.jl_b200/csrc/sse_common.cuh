@@ -1,0 +1,335 @@
+// sse_common.cuh — data layout and small helpers shared by the device code of the B200 SSE sweep backend (sm_100a).
+//
+// Execution model (round 2): ONE persistent CTA per SM (sse::k_sweep, sse_sweep.cuh) owns a fixed subset of the walkers.
+// Its warps have two roles:
+//   * worm warps    — ONE LANE advances ONE walker's worm update (src/sse.jl:193-303): 32 independent dependent-load
+//                     chains per warp with divergent addresses, per-lane Philox stream, per-lane record registers
+//                     (sse_worm.cuh).  The chase is bound by DRAM latency and the random-sector rate, not by issue
+//                     slots, so a few worm warps per SM carry every chain the memory system can serve.
+//   * stream warps  — ONE WARP advances ONE walker through the streaming phases: the end of worm_update (controller +
+//                     state rebuild), Carlo.measure!, diagonal_update fused with make_vertex_list! (sse_stream.cuh).
+// Walkers move between the two roles through a per-CTA status table in shared memory; nothing synchronises walkers
+// with each other, and a walker can be parked anywhere in its worm phase when its visit budget for the launch runs out
+// (a monster worm only delays its own walker).
+//
+// Per-walker data in HBM:
+//   words[W][Mw_cap]  uint2  {bits, rank}: occupancy bitmap of 32 slots of the padded operator string (bit p%32 of word
+//                            p/32 set <=> slot p holds a non-identity operator) and the number of non-identity slots
+//                            before the word.  Replaces the reference's 8 B/slot `operators` (src/sse.jl:12) for
+//                            identity slots: 0.25 B per slot.  A worm start (sse.jl:241-247) is ONE 8-byte load.
+//   rec  [W][R_cap]   uint4  16-byte vertex record of the k-th non-identity operator: {op code, 4 x 24-bit leg links
+//                            (k' << 2 | leg')}.  Replaces the 8 B op code + 64 B/slot `vertices` (vertex_list.jl:1-13).
+//                            The record array is a RING: generation g occupies [G, G + n) mod R_cap, and the diagonal
+//                            update writes generation g+1 right behind it ([G + n, ...)), reading the old op codes just
+//                            ahead of its own write head, so no second buffer exists.
+//   state[W][N] u8, vfirst[W][N] u32 (link of the first leg on each site's world line; NONE32 = no operator),
+//   vlast[W][N] u32 (scratch of the record build), ctl[W] = every scalar of the walker (WalkerCtl, 128 B).
+// Device op code (u32): bit0 = 1, bit1 = diagonal, bits 2..13 = global vertex id, bits 14..31 = bond.
+//
+// Every phase reproduces the reference's draw ORDER and its Float64 expressions (compile with
+// -fmad=false), so results are bit-identical to the CPU oracle under the same random stream.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/sse_b200.h"
+#include "../../include/sse_rng.h"
+
+namespace sse {
+
+constexpr uint32_t FULL = 0xffffffffu;
+constexpr uint32_t NONE32 = 0xffffffffu;
+constexpr uint32_t NONE24 = 0x00ffffffu;
+constexpr int VBITS = 12;                              // global vertex id bits in the device op code
+constexpr uint32_t VMASK = ((1u << VBITS) - 1u) << 2;  // bits 2..13
+constexpr int BOND_SHIFT = 2 + VBITS;                  // 14
+constexpr int RNG_WORDS = 66;                          // 33 Philox blocks x 2 draws (see phase_diag_build)
+constexpr int PHASE_WARPS = 4;                         // warps per CTA of sse::k_phase (one warp = one walker)
+constexpr int SWEEP_MAX_WARPS = 24;                    // warps per CTA of sse::k_sweep (launch bounds 768 x 1)
+constexpr int ROT_MARGIN = 64;                         // ring slack kept between the write head and unread old records
+
+__host__ __device__ __forceinline__ uint32_t op_pack(uint32_t bond, uint32_t gv, uint32_t diag) {
+    return 1u | (diag << 1) | (gv << 2) | (bond << BOND_SHIFT);
+}
+__host__ __device__ __forceinline__ uint32_t op_gv(uint32_t op) { return (op >> 2) & ((1u << VBITS) - 1u); }
+__host__ __device__ __forceinline__ uint32_t op_bond(uint32_t op) { return op >> BOND_SHIFT; }
+
+// Shared-memory image of the vertex tables (built once on the host, copied per CTA).
+struct TabLayout {
+    int bytes;
+    int off_t1;       // uint4  [nv*max_worm*4] first outcome fused with the transition header:
+                      //        {cumprob0 lo, cumprob0 hi, packed step0, dim_out << 24 | offset of outcome 1 << 6 | remaining count}
+    int off_outc;     // uint4  [n_outcomes] {cumprob lo, cumprob hi, packed step, dim_out << 24}
+    int off_weights;  // double [nv]
+    int off_vinfo;    // u32    [nv]  leg states packed, 8 bits per leg
+    int off_diagv;    // u16    [n_diag]  global vertex id + 1, 0 = invalid
+    int off_vneg;     // u8     [nv]  1 if the vertex sign is negative
+};
+// packed step (t1[].z / outc[].z): bits 1..13 = vertex bits of the op code (diag << 1 | gv << 2), bits 16..17 = exit leg,
+// bits 24..31 = exit worm;  .w: bits 24..31 = dim of the exit leg's site, (t1 only) bits 6..23 = offset of the 2nd outcome,
+// bits 0..5 = number of further outcomes.
+struct SmTab {
+    const uint4 *t1;
+    const uint4 *outc;
+    const double *weights;
+    const uint32_t *vinfo;
+    const uint16_t *diagv;
+    const uint8_t *vneg;
+    uint32_t t1_s, outc_s;  // shared-space addresses of t1 / outc
+};
+
+struct DevModel {
+    int n_sites, n_bonds, nv, max_worm, n_est, est_max_dim, norm_sites;
+    double energy_offset;
+    const uint4 *bond_info;   // [n_bonds] {site_a | dim_a << 24, site_b | dim_b << 24, diag table base, type}
+    const uint8_t *site_dim;  // [n_sites]
+    const double *est_values; // [n_est][n_sites][est_max_dim]
+    const uint8_t *tab_blob;  // TabLayout image
+    TabLayout tl;
+};
+
+// Every scalar of one walker: the reference's `MC` fields (src/sse.jl:6-24), the stream position, and the progress of
+// the sweep in flight (so a launch can stop anywhere in the worm phase and the next one resumes there).
+struct __align__(16) WalkerCtl {
+    double T;
+    double num_worms;
+    double avg_wl;
+    double last_wlf;
+    unsigned long long draws;         // stream position
+    unsigned long long sweep_visits;  // sum of the lengths of this sweep's finished worms
+    unsigned long long worm_len;      // parked worm: length so far (worm_traverse!'s `worm_length`)
+    unsigned long long budget_left;   // worm visits this walker may still do in the current launch series
+    unsigned long long sweeps_done;   // completed sweeps since sse_init / sse_set_state
+    int M, n;
+    uint32_t G;                       // ring position of record 0 of the current generation
+    uint32_t flags;
+    uint32_t phase;                   // 0 = between sweeps, 1 = worm phase of a sweep in progress
+    uint32_t worms_left;              // worms of this sweep not yet finished (incl. a parked one)
+    uint32_t inworm;                  // 1 = parked in the middle of a worm: pos / wf / pos0 / w0 / worm_len are valid
+    uint32_t pos, wf, pos0, w0;       // parked worm: current leg link, current worm, start leg link, start worm
+    int32_t sweeps_left;              // sweeps still to do in the current sse_sweep call
+    uint32_t pad_[2];
+};
+static_assert(sizeof(WalkerCtl) == 128, "WalkerCtl is one 128-byte line");
+
+struct DevWalkers {
+    int W;
+    int64_t M_cap;               // slots (multiple of 32)
+    int64_t Mw_cap;              // words = M_cap / 32
+    int64_t n_cap;               // max non-identity operators
+    int64_t R_cap;               // ring size in records (> n_cap)
+    uint2 *words;
+    uint4 *rec;
+    uint8_t *state;
+    uint8_t *mark;               // [W][N] scratch, only when a stream warp's arrays do not fit in shared memory
+    uint32_t *vfirst, *vlast;
+    WalkerCtl *ctl;
+    double *acc;                 // [W][n_obs]
+    long long *acc_cnt;          // [W][2]
+    unsigned long long *counters;// [SSE_N_COUNTERS]
+    long long *dbg_len;          // [W] worm length of the last sse_dbg_worm_traverse
+    double *obs_out;             // [W][n_obs] scratch for sse_measure
+    const unsigned long long *inj;
+    long long inj_len;
+    unsigned long long seed, wid_off;
+    double twlf, atten;
+    int n_obs;
+};
+
+constexpr uint32_t FATAL_FLAGS = SSE_FLAG_M_OVERFLOW | SSE_FLAG_N_OVERFLOW | SSE_FLAG_STREAM_EXHAUSTED;
+
+// Context of one walker inside a streaming phase (uniform across the warp).
+struct Ctx {
+    uint2 *words;
+    uint4 *rec;
+    uint8_t *state;              // generic pointer: shared memory or the global array
+    uint8_t *mark;
+    unsigned long long *rng;     // per-warp shared scratch, RNG_WORDS entries
+    uint32_t *vfirst, *vlast;
+    const unsigned long long *inj;
+    long long inj_len;
+    unsigned long long seed, wid, draws;
+    double T, num_worms, avg_wl, last_wlf;
+    int M, n;
+    uint32_t G, Rcap, flags, lane;
+};
+
+// The inline-PTX helpers below are the only non-C++ code of the device side; the test-only warp emulator
+// (tests/emu/cuda_emu.h) provides host versions and defines SSE_PTX_HELPERS_PROVIDED.
+#ifndef SSE_PTX_HELPERS_PROVIDED
+__device__ __forceinline__ uint32_t lanemask_lt() {
+    uint32_t m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
+// per-lane accesses of the worm phase: every lane touches its own walker
+__device__ __forceinline__ uint4 lane_ld128(const uint4 *p) {
+    uint4 v;
+    asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint2 lane_ld64(const uint2 *p) {
+    uint2 v;
+    asm volatile("ld.global.cg.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void lane_st32(void *p, uint32_t v) {
+    asm volatile("st.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_volatile_shared(const uint32_t *p) {
+    return *reinterpret_cast<const volatile uint32_t *>(p);
+}
+__device__ __forceinline__ void st_volatile_shared(uint32_t *p, uint32_t v) { *reinterpret_cast<volatile uint32_t *>(p) = v; }
+__device__ __forceinline__ void backoff(unsigned ns) { __nanosleep(ns); }
+#endif
+
+// ring position of logical record k of the generation that starts at G
+__device__ __forceinline__ uint32_t ring(uint32_t G, uint32_t Rcap, uint32_t k) {
+    const uint32_t i = G + k;
+    return i >= Rcap ? i - Rcap : i;
+}
+
+// leg link j (24 bits) of a record: bits [24j, 24j+24) of the 96-bit little-endian field (y, z, w)
+__device__ __forceinline__ uint32_t rec_link(const uint4 &r, uint32_t j) {
+    const uint32_t lo = (j < 2) ? r.y : ((j == 2) ? r.z : r.w);
+    const uint32_t hi = (j < 2) ? r.z : r.w;
+    return __funnelshift_r(lo, hi, (24u * j) & 31u) & NONE24;
+}
+__host__ __device__ __forceinline__ uint4 rec_pack(uint32_t op, uint32_t l0, uint32_t l1, uint32_t l2, uint32_t l3) {
+    uint4 r;
+    r.x = op;
+    r.y = l0 | (l1 << 24);
+    r.z = (l1 >> 8) | (l2 << 16);
+    r.w = (l2 >> 16) | (l3 << 8);
+    return r;
+}
+// overwrite the leg link named by `target` (k << 2 | leg) of the generation at G with `value` (three byte stores)
+__device__ __forceinline__ void rec_patch(uint4 *rec, uint32_t G, uint32_t Rcap, uint32_t target, uint32_t value) {
+    uint8_t *b = reinterpret_cast<uint8_t *>(rec + ring(G, Rcap, target >> 2)) + 4u + 3u * (target & 3u);
+    b[0] = (uint8_t)value;
+    b[1] = (uint8_t)(value >> 8);
+    b[2] = (uint8_t)(value >> 16);
+}
+
+__device__ __forceinline__ double shfl_f64(double v, int src) {
+    int lo = __double2loint(v), hi = __double2hiint(v);
+    lo = __shfl_sync(FULL, lo, src);
+    hi = __shfl_sync(FULL, hi, src);
+    return __hiloint2double(hi, lo);
+}
+__device__ __forceinline__ double shfl_up_f64(double v, int d) {
+    int lo = __double2loint(v), hi = __double2hiint(v);
+    lo = __shfl_up_sync(FULL, lo, d);
+    hi = __shfl_up_sync(FULL, hi, d);
+    return __hiloint2double(hi, lo);
+}
+__device__ __forceinline__ double warp_sum_f64(double v) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        int lo = __double2loint(v), hi = __double2hiint(v);
+        lo = __shfl_xor_sync(FULL, lo, d);
+        hi = __shfl_xor_sync(FULL, hi, d);
+        v += __hiloint2double(hi, lo);
+    }
+    return v;
+}
+__device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(FULL, v, d);
+    return v;
+}
+
+__device__ __forceinline__ SmTab stage_tables(const DevModel &dm, uint8_t *smem) {
+    const int n16 = dm.tl.bytes >> 4;
+    const uint4 *src = reinterpret_cast<const uint4 *>(dm.tab_blob);
+    uint4 *dst = reinterpret_cast<uint4 *>(smem);
+    for (int i = threadIdx.x; i < n16; i += blockDim.x) dst[i] = __ldg(src + i);
+    __syncthreads();
+    SmTab st;
+    st.t1 = reinterpret_cast<const uint4 *>(smem + dm.tl.off_t1);
+    st.outc = reinterpret_cast<const uint4 *>(smem + dm.tl.off_outc);
+    st.weights = reinterpret_cast<const double *>(smem + dm.tl.off_weights);
+    st.vinfo = reinterpret_cast<const uint32_t *>(smem + dm.tl.off_vinfo);
+    st.diagv = reinterpret_cast<const uint16_t *>(smem + dm.tl.off_diagv);
+    st.vneg = reinterpret_cast<const uint8_t *>(smem + dm.tl.off_vneg);
+    st.t1_s = (uint32_t)__cvta_generic_to_shared(st.t1);
+    st.outc_s = (uint32_t)__cvta_generic_to_shared(st.outc);
+    return st;
+}
+
+// bytes of shared scratch of one streaming warp: random draws + (level 1) state[N], mark[N]
+__host__ __device__ inline int stream_scratch_bytes(int n_sites, int level) {
+    int b = ((RNG_WORDS * 8) + 15) & ~15;
+    if (level >= 1) b += 2 * ((n_sites + 15) & ~15);
+    return b;
+}
+
+// Open / close the streaming context of walker w.  state[] is staged in the warp's shared scratch at level 1.
+__device__ __forceinline__ Ctx ctx_open(const DevModel &dm, const DevWalkers &dw, int w, uint8_t *scratch, int level, uint32_t lane) {
+    const int N = dm.n_sites;
+    Ctx c;
+    c.lane = lane;
+    c.rng = reinterpret_cast<unsigned long long *>(scratch);
+    uint8_t *gstate = dw.state + (size_t)w * N;
+    if (level) {
+        c.state = scratch + (((RNG_WORDS * 8) + 15) & ~15);
+        c.mark = c.state + ((N + 15) & ~15);
+    } else {
+        c.state = gstate;
+        c.mark = dw.mark + (size_t)w * N;
+    }
+    c.words = dw.words + (size_t)w * dw.Mw_cap;
+    c.rec = dw.rec + (size_t)w * dw.R_cap;
+    c.vfirst = dw.vfirst + (size_t)w * N;
+    c.vlast = dw.vlast + (size_t)w * N;
+    c.inj = dw.inj ? dw.inj + (size_t)w * dw.inj_len : nullptr;
+    c.inj_len = dw.inj_len;
+    c.seed = dw.seed;
+    c.wid = dw.wid_off + (unsigned long long)w;
+    const WalkerCtl *ctl = dw.ctl + w;
+    c.draws = __ldcg(&ctl->draws);
+    c.T = __ldcg(&ctl->T);
+    c.num_worms = __ldcg(&ctl->num_worms);
+    c.avg_wl = __ldcg(&ctl->avg_wl);
+    c.last_wlf = __ldcg(&ctl->last_wlf);
+    c.M = __ldcg(&ctl->M);
+    c.n = __ldcg(&ctl->n);
+    c.G = __ldcg(&ctl->G);
+    c.flags = __ldcg(&ctl->flags);
+    c.Rcap = (uint32_t)dw.R_cap;
+    for (int s = lane; s < N; s += 32) {
+        if (level) c.state[s] = __ldcg(gstate + s);
+        c.mark[s] = 0;
+    }
+    __syncwarp();
+    return c;
+}
+__device__ __forceinline__ void ctx_close(const DevModel &dm, const DevWalkers &dw, int w, int level, const Ctx &c) {
+    const int N = dm.n_sites;
+    __syncwarp();
+    if (level) {
+        uint8_t *gstate = dw.state + (size_t)w * N;
+        for (int s = c.lane; s < N; s += 32) gstate[s] = c.state[s];
+    }
+    if (c.lane == 0) {
+        WalkerCtl *ctl = dw.ctl + w;
+        ctl->draws = c.draws;
+        ctl->T = c.T;
+        ctl->num_worms = c.num_worms;
+        ctl->avg_wl = c.avg_wl;
+        ctl->last_wlf = c.last_wlf;
+        ctl->M = c.M;
+        ctl->n = c.n;
+        ctl->G = c.G;
+        ctl->flags = c.flags;
+        if (c.flags & FATAL_FLAGS) atomicOr(reinterpret_cast<unsigned long long *>(dw.counters + SSE_CNT_ANY_FATAL), 1ull);
+    }
+    __syncwarp();
+}
+
+}  // namespace sse

@@ -1,0 +1,502 @@
+// sse_stream.cuh — the streaming phases, executed by ONE WARP for ONE walker (32 string slots per step):
+//   phase_diag_build   diagonal_update (src/sse.jl:137-191) fused with make_vertex_list! (src/vertex_list.jl:15-54)
+//   worm_finish        the end of worm_update (src/sse.jl:200-228): WormLengthFraction, controller, state rebuild
+//   phase_measure      Carlo.measure! (src/sse.jl:70-87): measure_sign, scalar observables, measure_opstring!
+// Warp primitives do the scans: ballot/popc prefix sums give each slot its random-stream offset (2/1/0 draws by
+// pre-update slot type) and its compact record index; one Philox block per lane feeds a whole chunk; shuffles resolve
+// same-site ordering only in the rare chunks where two operators share a site.
+#pragma once
+#include "sse_common.cuh"
+
+namespace sse {
+
+template <bool INJ>
+__device__ __forceinline__ uint64_t draw(const Ctx &c, unsigned long long k) {
+    if (INJ) return (long long)k < c.inj_len ? (uint64_t)__ldg(c.inj + k) : 0ull;
+    return sse_philox_draw(c.seed, c.wid, k);
+}
+// Fill the warp's scratch with the draws [2*j0, 2*j0 + 64): lane L computes Philox block j0 + L (two draws).
+template <bool INJ>
+__device__ __forceinline__ void fill_draws(const Ctx &c, unsigned long long j0) {
+    if (!INJ) {
+        uint32_t b[4];
+        sse_philox_block(c.seed, c.wid, j0 + c.lane, b);
+        reinterpret_cast<uint4 *>(c.rng)[c.lane] = make_uint4(b[0], b[1], b[2], b[3]);
+    }
+}
+// Draw with absolute index k from the scratch filled by fill_draws(j0) (or from the injected stream).
+template <bool INJ>
+__device__ __forceinline__ uint64_t scratch_draw(const Ctx &c, unsigned long long j0, unsigned long long k) {
+    if (INJ) return (long long)k < c.inj_len ? (uint64_t)__ldg(c.inj + k) : 0ull;
+    return c.rng[k - 2ull * j0];
+}
+
+// Sequential reader of a walker's operator string: per 32-slot chunk every lane gets the op code of its slot (0 =
+// identity), gathered from the record ring through the occupancy bitmap.  The bitmap words of 32 chunks are held one
+// per lane (the next 32 are already requested), the op codes of the next chunk are requested one step ahead.
+struct OpReader {
+    const uint2 *words;
+    const uint4 *rec;
+    uint32_t G, Rcap, lane, lt;
+    int nchunks;
+    uint32_t wcur, wnext, bits_next, op_next, kold;
+
+    __device__ __forceinline__ uint32_t word_at(int ch) const { return ch < nchunks ? __ldcg(&words[ch].x) : 0u; }
+    __device__ __forceinline__ uint32_t op_at(uint32_t bits, uint32_t k0) const {
+        return ((bits >> lane) & 1u) ? __ldcg(&rec[ring(G, Rcap, k0 + __popc(bits & lt))].x) : 0u;
+    }
+    __device__ __forceinline__ void init(const uint2 *words_, const uint4 *rec_, uint32_t G_, uint32_t Rcap_, int nchunks_,
+                                         uint32_t lane_) {
+        words = words_;
+        rec = rec_;
+        G = G_;
+        Rcap = Rcap_;
+        lane = lane_;
+        lt = lanemask_lt();
+        nchunks = nchunks_;
+        wcur = word_at((int)lane);
+        wnext = word_at(32 + (int)lane);
+        kold = 0;
+        bits_next = __shfl_sync(FULL, wcur, 0);
+        op_next = op_at(bits_next, 0);
+    }
+    // chunk ch (called for ch = 0, 1, 2, ... in order): bits = occupancy of its 32 slots, op = this lane's op code;
+    // returns the index of the chunk's first record
+    __device__ __forceinline__ uint32_t next(int ch, uint32_t &bits, uint32_t &op) {
+        bits = bits_next;
+        op = op_next;
+        const uint32_t k0 = kold;
+        kold += __popc(bits);
+        if ((ch & 31) == 31) {
+            wcur = wnext;
+            wnext = word_at(ch + 33 + (int)lane);
+        }
+        bits_next = __shfl_sync(FULL, wcur, (ch + 1) & 31);
+        if (ch + 1 >= nchunks) bits_next = 0u;
+        op_next = op_at(bits_next, kold);
+        return k0;
+    }
+};
+
+// ------------------------------------------------------------------------------------------------------
+// diagonal_update (src/sse.jl:137-191) fused with make_vertex_list! (src/vertex_list.jl:15-54).
+// do_diag = false rebuilds the records of the unchanged string (make_vertex_list! alone).
+// Reads generation g of the record ring (op codes only) and writes generation g+1 (op codes + links) behind it.
+// ------------------------------------------------------------------------------------------------------
+template <bool INJ>
+__device__ void phase_diag_build(const SmTab &st, const DevModel &dm, const DevWalkers &dw, Ctx &c, bool do_diag) {
+    const uint32_t lane = c.lane, lt = lanemask_lt();
+    const int N = dm.n_sites;
+    if (do_diag && 2ll * (long long)c.n >= (long long)c.M) {  // n >= 0.5*M  (sse.jl:138)
+        long long newM = (3ll * (long long)c.M) / 2 + 100;     // floor(1.5*M + 100) (sse.jl:143)
+        if (newM > dw.M_cap) { c.flags |= SSE_FLAG_M_OVERFLOW; return; }
+        c.M = (int)newM;  // slots beyond the old M are identity by invariant (sse.jl:144)
+    }
+    for (int s = lane; s < N; s += 32) { c.vfirst[s] = NONE32; c.vlast[s] = NONE32; }
+    __syncwarp();
+    const int M = c.M;
+    const uint32_t Nb = (uint32_t)dm.n_bonds;
+    const double p_make_bond_raw = (double)dm.n_bonds / c.T;   // sse.jl:147
+    const double p_remove_bond_raw = c.T / (double)dm.n_bonds; // sse.jl:148
+    const uint32_t Rcap = c.Rcap, n_old = (uint32_t)c.n;
+    const uint32_t Gn = ring(c.G, Rcap, n_old);  // the new generation starts right behind the old one
+    int n = c.n;
+    uint32_t kbase = 0;
+    unsigned long long draws = c.draws;
+    const int nchunks = (M + 31) >> 5;
+    OpReader rd;
+    rd.init(c.words, c.rec, c.G, Rcap, nchunks, lane);
+    uint2 wout = make_uint2(0u, 0u);  // new {bits, rank} of chunk 32*j + lane, written 32 words at a time
+
+    for (int ch = 0; ch < nchunks; ++ch) {
+        const int p = ch * 32 + (int)lane;
+        const bool active = p < M;
+        uint32_t obits, op;
+        const uint32_t kold0 = rd.next(ch, obits, op);
+        const bool nonid = op != 0u;
+        const bool is_id = active && !nonid;
+        const bool is_dg = nonid && (op & 2u);
+        const bool is_off = nonid && !(op & 2u);
+        uint32_t bond = op_bond(op);
+        const uint32_t gv = op_gv(op);
+        uint32_t newop = op;
+        double r = 0.0;
+        uint32_t idm = 0, dgm = 0;
+
+        if (do_diag) {
+            // stream offsets: 2 draws per identity slot, 1 per diagonal operator, in slot order (Appendix A)
+            idm = __ballot_sync(FULL, is_id);
+            dgm = __ballot_sync(FULL, is_dg);
+            const uint32_t D = 2u * __popc(idm) + __popc(dgm);
+            if (D) {
+                const unsigned long long my = draws + 2u * __popc(idm & lt) + __popc(dgm & lt);
+                const unsigned long long j0 = draws >> 1;
+                fill_draws<INJ>(c, j0);
+                if (!INJ && (draws & 1ull) && D == 64u && lane == 0) {  // the one draw beyond 32 blocks
+                    uint32_t b[4];
+                    sse_philox_block(c.seed, c.wid, j0 + 32, b);
+                    reinterpret_cast<uint4 *>(c.rng)[32] = make_uint4(b[0], b[1], b[2], b[3]);
+                }
+                __syncwarp();
+                if (is_id) {
+                    bond = (uint32_t)sse_uint_below(scratch_draw<INJ>(c, j0, my), Nb);  // rand(rng, 1:N_b) - 1 (sse.jl:152)
+                    r = sse_u01(scratch_draw<INJ>(c, j0, my + 1));                      // sse.jl:166
+                } else if (is_dg) {
+                    r = sse_u01(scratch_draw<INJ>(c, j0, my));                          // sse.jl:178
+                }
+                draws += D;
+            }
+        }
+        uint4 bi = make_uint4(0, 0, 0, 0);
+        if (is_id || nonid) bi = __ldg(dm.bond_info + bond);
+        const uint32_t sa = bi.x & NONE24, sb = bi.y & NONE24;
+
+        if (do_diag) {
+            // State seen by each identity slot = state at chunk start overridden by earlier off-diagonal
+            // operators of this chunk (sse.jl:182-188).  Off-diagonal lanes tag their sites in mark[]; only if
+            // an identity lane reads a tagged site, or two off-diagonal lanes share a site, the in-order
+            // shuffle loop runs.
+            const uint32_t offm = __ballot_sync(FULL, is_off);
+            uint32_t s_a = 1, s_b = 1, ta = 0, tb = 0;
+            if (offm) {
+                const uint8_t tag = (uint8_t)(0x80u | lane);
+                if (is_off) {
+                    const uint32_t vi = st.vinfo[gv];
+                    ta = (vi >> 16) & 0xffu;
+                    tb = vi >> 24;
+                    c.mark[sa] = tag;
+                    c.mark[sb] = tag;
+                }
+                __syncwarp();
+                bool hit = false;
+                if (is_off) hit = (c.mark[sa] != tag) || (c.mark[sb] != tag);
+                if (is_id) {
+                    hit = ((c.mark[sa] | c.mark[sb]) & 0x80u) != 0;
+                    s_a = c.state[sa];
+                    s_b = c.state[sb];
+                }
+                const uint32_t anyhit = __ballot_sync(FULL, hit);
+                __syncwarp();
+                bool wa = is_off, wb = is_off;
+                if (anyhit) {
+                    for (uint32_t m = offm; m;) {
+                        const int L = __ffs(m) - 1;
+                        m &= m - 1;
+                        const uint32_t qa = __shfl_sync(FULL, sa, L), qb = __shfl_sync(FULL, sb, L);
+                        const uint32_t qta = __shfl_sync(FULL, ta, L), qtb = __shfl_sync(FULL, tb, L);
+                        if (is_id && (int)lane > L) {
+                            if (sa == qa) s_a = qta;
+                            if (sa == qb) s_a = qtb;
+                            if (sb == qa) s_b = qta;
+                            if (sb == qb) s_b = qtb;
+                        }
+                        if (is_off && (int)lane < L) {  // a later operator of the chunk overwrites this site
+                            if (sa == qa || sa == qb) wa = false;
+                            if (sb == qa || sb == qb) wb = false;
+                        }
+                    }
+                }
+                if (is_off) {
+                    if (wa) c.state[sa] = (uint8_t)ta;
+                    if (wb) c.state[sb] = (uint8_t)tb;
+                    c.mark[sa] = 0;
+                    c.mark[sb] = 0;
+                }
+            } else if (is_id) {
+                s_a = c.state[sa];
+                s_b = c.state[sb];
+            }
+
+            double w = 0.0;
+            uint32_t gvnew = 0;
+            if (is_id) {
+                // join_idx (util.jl:15-23) -> diagonal vertex -> weight (sse.jl:156-162)
+                const uint32_t cidx = bi.z + (s_a - 1u) + (bi.x >> 24) * (s_b - 1u);
+                const uint32_t dv = st.diagv[cidx];
+                if (dv) { gvnew = dv - 1u; w = st.weights[gvnew]; }
+            } else if (is_dg) {
+                w = st.weights[gv];
+            }
+            // Accept tests (sse.jl:164-166,176-178) depend on the running operator count n.  Within the chunk
+            // n stays in [n - #diagonal, n + #identity]; both tests are monotone in n (IEEE division and
+            // multiplication are monotone), so evaluating them at the two ends decides every lane whose draw is
+            // not between the two thresholds.  Only if some lane is undecided (probability ~ 64/(M-n) per chunk)
+            // the in-order recurrence is solved exactly by fixed-point iteration.
+            const int n_lo = n - __popc(dgm), n_hi = n + __popc(idm);
+            bool acc = false, amb = false;
+            if (is_id) {
+                const double pm_lo = p_make_bond_raw / (double)(M - n_lo);
+                const double pm_hi = (M - n_hi > 0) ? p_make_bond_raw / (double)(M - n_hi) : __longlong_as_double(0x7ff0000000000000ll);
+                acc = r < pm_lo * w;
+                amb = !acc && (r < pm_hi * w);
+            } else if (is_dg) {
+                const double rw = r * w;
+                acc = rw < (double)(M - n_hi + 1) * p_remove_bond_raw;
+                amb = !acc && (rw < (double)(M - n_lo + 1) * p_remove_bond_raw);
+            }
+            uint32_t ins, rem;
+            if (__ballot_sync(FULL, amb)) {
+                // lane l only depends on lanes < l: after i rounds the first i lanes are final
+                ins = 0;
+                rem = 0;
+                while (true) {
+                    const int nl = n + __popc(ins & lt) - __popc(rem & lt);
+                    bool a2 = false;
+                    if (is_id) {
+                        const double p_make_bond = p_make_bond_raw / (double)(M - nl);  // sse.jl:164
+                        a2 = r < p_make_bond * w;                                        // sse.jl:166
+                    } else if (is_dg) {
+                        const double p_remove_bond = (double)(M - nl + 1) * p_remove_bond_raw;  // sse.jl:176-177
+                        a2 = r * w < p_remove_bond;                                              // sse.jl:178
+                    }
+                    const uint32_t ins2 = __ballot_sync(FULL, is_id && a2), rem2 = __ballot_sync(FULL, is_dg && a2);
+                    if (ins2 == ins && rem2 == rem) break;
+                    ins = ins2;
+                    rem = rem2;
+                }
+            } else {
+                ins = __ballot_sync(FULL, is_id && acc);
+                rem = __ballot_sync(FULL, is_dg && acc);
+            }
+            n += __popc(ins) - __popc(rem);
+            if (is_id && ((ins >> lane) & 1u)) newop = op_pack(bond, gvnew, 1u);
+            if (is_dg && ((rem >> lane) & 1u)) newop = 0u;
+        }
+
+        // ---- records of the new generation ----
+        const bool nn = newop != 0u;
+        const uint32_t nm = __ballot_sync(FULL, nn);
+        const uint32_t cnt = __popc(nm);
+        const uint32_t k = kbase + __popc(nm & lt);
+        // capacity: n_cap records, and the write head must stay clear of old records that are not consumed yet (this
+        // chunk's are in registers, the next chunk's are requested: ROT_MARGIN covers both)
+        if ((long long)kbase + cnt > dw.n_cap ||
+            (long long)n_old + kbase + cnt + ROT_MARGIN > (long long)Rcap + kold0) {
+            c.flags |= SSE_FLAG_N_OVERFLOW;
+            return;
+        }
+        // same-site collisions inside the chunk are rare: every operator tags its two sites, a lost tag
+        // reveals a collision, and only then the nearest earlier / later operator on each site is searched
+        uint32_t pa = NONE24, pb = NONE24, sua = NONE24, sub = NONE24;
+        if (nn) {
+            c.mark[sa] = (uint8_t)lane;
+            c.mark[sb] = (uint8_t)lane;
+        }
+        __syncwarp();
+        const bool lost_a = nn && c.mark[sa] != (uint8_t)lane, lost_b = nn && c.mark[sb] != (uint8_t)lane;
+        if (__ballot_sync(FULL, lost_a || lost_b)) {
+            // losers flag the contested sites; every operator on a flagged site takes part in the search
+            __syncwarp();
+            if (lost_a) c.mark[sa] = 0x7f;
+            if (lost_b) c.mark[sb] = 0x7f;
+            __syncwarp();
+            const bool inv = nn && (c.mark[sa] == 0x7f || c.mark[sb] == 0x7f);
+            for (uint32_t m = __ballot_sync(FULL, inv); m;) {
+                const int L = __ffs(m) - 1;
+                m &= m - 1;
+                const uint32_t qa = __shfl_sync(FULL, sa, L), qb = __shfl_sync(FULL, sb, L);
+                const uint32_t qk = __shfl_sync(FULL, k, L) << 2;
+                if (nn && (int)lane > L) {
+                    if (sa == qa) pa = qk | 2u;
+                    if (sa == qb) pa = qk | 3u;
+                    if (sb == qa) pb = qk | 2u;
+                    if (sb == qb) pb = qk | 3u;
+                } else if (nn && (int)lane < L) {
+                    if (sua == NONE24) { if (sa == qa) sua = qk; else if (sa == qb) sua = qk | 1u; }
+                    if (sub == NONE24) { if (sb == qa) sub = qk; else if (sb == qb) sub = qk | 1u; }
+                }
+            }
+        }
+        uint32_t ma = NONE32, mb = NONE32;
+        if (nn) {
+            if (pa == NONE24) ma = c.vlast[sa];
+            if (pb == NONE24) mb = c.vlast[sb];
+        }
+        __syncwarp();
+        if (nn) {
+            const uint32_t me = k << 2;
+            uint32_t bla = pa, blb = pb;
+            if (pa == NONE24) {
+                if (ma != NONE32) { bla = ma; rec_patch(c.rec, Gn, Rcap, ma, me); }  // vertices[s1,p1] = (s,p) (vertex_list.jl:36-38)
+                else c.vfirst[sa] = me;                                               // vertex_list.jl:40
+            }
+            if (pb == NONE24) {
+                if (mb != NONE32) { blb = mb; rec_patch(c.rec, Gn, Rcap, mb, me | 1u); }
+                else c.vfirst[sb] = me | 1u;
+            }
+            if (sua == NONE24) c.vlast[sa] = me | 2u;  // vertex_list.jl:42
+            if (sub == NONE24) c.vlast[sb] = me | 3u;
+            c.rec[ring(Gn, Rcap, k)] = rec_pack(newop, bla, blb, sua, sub);  // forward links still unknown stay NONE24 until patched
+        }
+        if (lane == (uint32_t)(ch & 31)) wout = make_uint2(nm, kbase);
+        if ((ch & 31) == 31 || ch == nchunks - 1) {
+            const int wi = (ch & ~31) + (int)lane;
+            if (wi <= ch) c.words[wi] = wout;
+        }
+        kbase += cnt;
+        __syncwarp();
+    }
+    // periodic closure (vertex_list.jl:46-51)
+    for (int s = lane; s < N; s += 32) {
+        const uint32_t f = c.vfirst[s];
+        if (f != NONE32) {
+            const uint32_t l = c.vlast[s];
+            rec_patch(c.rec, Gn, Rcap, f, l);
+            rec_patch(c.rec, Gn, Rcap, l, f);
+        }
+    }
+    __syncwarp();
+    c.n = n;
+    c.G = Gn;
+    c.draws = draws;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// worm_update after the worms (src/sse.jl:200-228): WormLengthFraction, the worm-count controller, and the state
+// rebuild from the first leg on each site.  total = 1 + sum of the worm lengths (sse.jl:194-198).
+// ------------------------------------------------------------------------------------------------------
+template <bool INJ>
+__device__ void worm_finish(const SmTab &st, const DevModel &dm, const DevWalkers &dw, Ctx &c, bool thermalized, int widx,
+                            double total) {
+    const uint32_t lane = c.lane, lt = lanemask_lt();
+    if (thermalized && c.n != 0) {  // sse.jl:200-202
+        c.last_wlf = total / (double)c.n;
+        if (lane == 0) {
+            dw.acc[(size_t)widx * dw.n_obs + SSE_OBS_WORM_LENGTH_FRACTION] += c.last_wlf;
+            dw.acc_cnt[2 * widx + 1] += 1;
+        }
+    }
+    const double avg_worm_length = total / ceil(c.num_worms);  // sse.jl:204
+    if (!thermalized) {                                        // sse.jl:205-217
+        c.avg_wl += dw.atten * (avg_worm_length - c.avg_wl);
+        const double target_worms = dw.twlf * (double)c.n / c.avg_wl;
+        c.num_worms += dw.atten * (target_worms - c.num_worms + 100.0 * sse_tanh(target_worms - c.num_worms));
+        if (dw.atten != 0) {
+            const double lo = 1.0, hi = 1.0 + (double)c.n / 2.0;
+            c.num_worms = c.num_worms < lo ? lo : (c.num_worms > hi ? hi : c.num_worms);
+        }
+    }
+    // rebuild the state from the first leg on each site; untouched sites are redrawn IN SITE ORDER (sse.jl:219-228)
+    const int N = dm.n_sites;
+    __syncwarp();
+    for (int b = 0; b < N; b += 32) {
+        const int s = b + (int)lane;
+        const bool act = s < N;
+        const uint32_t f = act ? c.vfirst[s] : 0u;
+        const bool empty = act && f == NONE32;
+        const uint32_t em = __ballot_sync(FULL, empty);
+        if (empty) {
+            const uint32_t d = dm.site_dim[s];
+            c.state[s] = (uint8_t)(1u + (uint32_t)sse_uint_below(draw<INJ>(c, c.draws + __popc(em & lt)), d));
+        } else if (act) {
+            const uint32_t op = __ldcg(&c.rec[ring(c.G, c.Rcap, f >> 2)].x);
+            c.state[s] = (uint8_t)((st.vinfo[op_gv(op)] >> (8u * (f & 3u))) & 0xffu);
+        }
+        c.draws += __popc(em);
+    }
+    if (INJ && (long long)c.draws > c.inj_len) c.flags |= SSE_FLAG_STREAM_EXHAUSTED;
+    __syncwarp();
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Carlo.measure! (src/sse.jl:70-87): measure_sign (:305-314), the scalar observables, measure_opstring! (:321-376)
+// with the table-driven MagnetizationEstimator init/measure/result (magnetization_estimator.jl:96-230).
+// out[n_obs] (global) receives the observables.
+// ------------------------------------------------------------------------------------------------------
+__device__ void phase_measure(const SmTab &st, const DevModel &dm, const DevWalkers &dw, Ctx &c, double *out) {
+    const uint32_t lane = c.lane;
+    const int M = c.M;
+    const int nchunks = (M + 31) >> 5;
+    uint32_t neg = 0;
+    {
+        OpReader rd;
+        rd.init(c.words, c.rec, c.G, c.Rcap, nchunks, lane);
+        for (int ch = 0; ch < nchunks; ++ch) {
+            uint32_t bits, op;
+            rd.next(ch, bits, op);
+            neg += __popc(__ballot_sync(FULL, op != 0u && st.vneg[op_gv(op)]));
+        }
+    }
+    const double sign = (neg & 1u) ? -1.0 : 1.0;  // sse.jl:313
+    const double nops = (double)c.n;
+    if (lane == 0) {
+        out[SSE_OBS_SIGN] = sign;
+        out[SSE_OBS_OPERATOR_COUNT] = nops;
+        out[SSE_OBS_SIGN_OPERATOR_COUNT] = sign * nops;
+        out[SSE_OBS_SIGN_OPERATOR_COUNT2] = sign * (nops * nops);
+        out[SSE_OBS_SIGN_ENERGY] = -sign * (nops * c.T + dm.energy_offset) / (double)dm.norm_sites;
+        out[SSE_OBS_WORM_LENGTH_FRACTION] = c.last_wlf;
+    }
+    const int N = dm.n_sites, md = dm.est_max_dim;
+    for (int e = 0; e < dm.n_est; ++e) {
+        const double *ev = dm.est_values + (size_t)e * N * md;
+        // init (magnetization_estimator.jl:96-123)
+        double part = 0.0;
+        for (int s = lane; s < N; s += 32) part += __ldg(ev + (size_t)s * md + (c.state[s] - 1));
+        double tmpmag = warp_sum_f64(part);
+        double mag = 0, absmag = 0, mag2 = 0, mag4 = 0;  // per-lane partial sums
+        if (lane == 0) { mag = tmpmag; absmag = fabs(tmpmag); mag2 = tmpmag * tmpmag; mag4 = mag2 * mag2; }
+        OpReader rd;
+        rd.init(c.words, c.rec, c.G, c.Rcap, nchunks, lane);
+        for (int ch = 0; ch < nchunks; ++ch) {
+            uint32_t bits, op;
+            rd.next(ch, bits, op);
+            const bool nonid = op != 0u;
+            double delta = 0.0;
+            if (nonid && !(op & 2u)) {  // off-diagonal: tmpmag += sum_l sign*(m(top_l) - m(bottom_l)) (:134-150)
+                const uint4 bi = __ldg(dm.bond_info + op_bond(op));
+                const uint32_t vi = st.vinfo[op_gv(op)];
+                const double *ea = ev + (size_t)(bi.x & NONE24) * md, *eb = ev + (size_t)(bi.y & NONE24) * md;
+                delta = (__ldg(ea + ((vi >> 16) & 0xffu) - 1) - __ldg(ea + (vi & 0xffu) - 1)) +
+                        (__ldg(eb + (vi >> 24) - 1) - __ldg(eb + ((vi >> 8) & 0xffu) - 1));
+            }
+            const uint32_t offm = __ballot_sync(FULL, delta != 0.0);
+            double scan = delta;  // inclusive prefix sum over the chunk, in slot order
+            if (offm) {
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const double up = shfl_up_f64(scan, d);
+                    if ((int)lane >= d) scan += up;
+                }
+            }
+            if (nonid) {  // every non-identity operator is one sample (:152-158)
+                const double v = tmpmag + scan, v2 = v * v;
+                mag += v;
+                absmag += fabs(v);
+                mag2 += v2;
+                mag4 += v2 * v2;
+            }
+            if (offm) tmpmag += shfl_f64(scan, 31);
+        }
+        mag = warp_sum_f64(mag);
+        absmag = warp_sum_f64(absmag);
+        mag2 = warp_sum_f64(mag2);
+        mag4 = warp_sum_f64(mag4);
+        if (lane == 0) {  // result (:205-230)
+            const double ns = 1.0 + nops;
+            const double norm = 1.0 / (double)dm.norm_sites;
+            mag *= norm;
+            absmag *= norm;
+            mag2 *= norm * norm;
+            mag4 *= (norm * norm) * (norm * norm);
+            double *o = out + SSE_OBS_FIXED + SSE_OBS_PER_ESTIMATOR * e;
+            o[0] = sign * mag / ns;
+            o[1] = sign * absmag / ns;
+            o[2] = sign * mag2 / ns;
+            o[3] = sign * mag4 / ns;
+            o[4] = sign * (1.0 / c.T / (ns + 1.0) / ns * (mag * mag + mag2) * (double)dm.norm_sites);
+        }
+    }
+    __syncwarp();
+}
+
+// Add a walker's freshly measured observables to its accumulators (one sample of the bin).
+__device__ __forceinline__ void accumulate_obs(const DevWalkers &dw, int w, uint32_t lane, const double *out) {
+    __syncwarp();
+    for (int i = lane; i < dw.n_obs; i += 32)
+        if (i != SSE_OBS_WORM_LENGTH_FRACTION) dw.acc[(size_t)w * dw.n_obs + i] += out[i];
+    if (lane == 0) dw.acc_cnt[2 * w] += 1;
+    __syncwarp();
+}
+
+}  // namespace sse

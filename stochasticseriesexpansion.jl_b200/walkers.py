@@ -30,10 +30,6 @@ class DeviceModel:
         self.L = capi.lib()
         check(self.L.sse_model_create(C.byref(desc), C.byref(self.handle)))
 
-    def dbg_set_variant(self, variant: int):
-        """Tuning switches for A/B timing (2 = no hint prefetch, 4 = no hint pass); results never change."""
-        check(self.L.sse_dbg_set_variant(self.handle, int(variant)))
-
     def observable_names(self):
         names = list(OBS_FIXED)
         ests = self.model.get_opstring_estimators() if self.model is not None else []
@@ -108,6 +104,27 @@ class Walkers:
         if sync:
             self.sync()
 
+    def advance(self, visit_budget: int, max_sweeps: int = 2**31 - 1, thermalized: bool = False, measure: bool = False,
+                sync: bool = True):
+        """Free-running sweeps (sse_advance): every walker does `visit_budget` worm visits (or `max_sweeps` sweeps) and is
+        parked wherever it is; the next advance()/sweep() resumes there.  Same Markov chain per walker as sweep()."""
+        check(self.L.sse_advance(self.handle, int(max_sweeps), int(visit_budget), int(thermalized), int(measure)))
+        if sync:
+            self.sync()
+
+    def finish_sweeps(self, thermalized: bool = False, measure: bool = False, sync: bool = True):
+        """Complete the sweeps advance() left in flight (needed before get_state / measure / double_beta)."""
+        check(self.L.sse_finish_sweeps(self.handle, int(thermalized), int(measure)))
+        if sync:
+            self.sync()
+
+    def progress(self):
+        """(sweeps_done[n_walkers], in_flight[n_walkers]): completed sweeps since init/set_state, parked inside a sweep?"""
+        sd = np.zeros(self.n_walkers, dtype=np.uint64)
+        fl = np.zeros(self.n_walkers, dtype=np.uint8)
+        check(self.L.sse_get_progress(self.handle, sd.ctypes.data_as(u64p), fl.ctypes.data_as(u8p)))
+        return sd, fl.astype(bool)
+
     def sync(self):
         check(self.L.sse_sync(self.handle))
 
@@ -128,10 +145,11 @@ class Walkers:
         return s.value, c.value
 
     def fetch_counters(self, reset: bool = False) -> dict:
-        out = np.zeros(8, dtype=np.uint64)
+        out = np.zeros(16, dtype=np.uint64)
         check(self.L.sse_fetch_counters(self.handle, out.ctypes.data_as(u64p), int(reset)))
-        return dict(visits=int(out[0]), sweeps=int(out[1]), sum_n=int(out[2]), sum_M=int(out[3]),
-                    cycles_diag_build=int(out[4]), cycles_worm=int(out[5]), cycles_commit_measure=int(out[6]))
+        names = ("visits", "sweeps", "sum_n", "sum_M", "cycles_build", "cycles_worm", "cycles_finish", "cycles_idle",
+                 "lane_iters", "warp_iters", "tasks")
+        return {k: int(out[i]) for i, k in enumerate(names)}
 
     def get_state(self, walker: int) -> dict:
         ops = np.zeros(self.m_capacity + 32, dtype=np.uint64)
@@ -181,10 +199,10 @@ class Walkers:
         check(self.L.sse_set_temperature(self.handle, t.ctypes.data_as(f64p)))
         self.T = t
 
-    def set_walkers_per_warp(self, k: int):
-        """Launch shape of sweep(): 1 (default), 2 or 4 walkers per warp with interleaved worm updates.  Results are
-        bit-identical; the setting only matters for throughput of batches beyond ~4144 walkers per B200."""
-        check(self.L.sse_set_walkers_per_warp(self.handle, int(k)))
+    def set_launch_shape(self, worm_warps: int = 0, stream_warps: int = 0):
+        """Launch shape of sweep()/advance(): warps per CTA that chase worms (one lane = one walker) and warps that run the
+        streaming phases (one warp = one walker); 0 = automatic.  Results are bit-identical for every shape."""
+        check(self.L.sse_set_launch_shape(self.handle, int(worm_warps), int(stream_warps)))
 
     def set_controller(self, target_worm_length_fraction: float | None = None, num_worms_attenuation_factor: float | None = None):
         """The worm-count controller's two parameters (sse.jl:34-35), changeable between launches."""
@@ -254,6 +272,3 @@ class Walkers:
         check(self.L.sse_dbg_get_vertex_list(self.handle, walker, v.ctypes.data_as(i64p), M, vf.ctypes.data_as(i64p),
                                              vl.ctypes.data_as(i64p)))
         return v, vf, vl
-
-    def dbg_commit(self):
-        check(self.L.sse_dbg_commit(self.handle))

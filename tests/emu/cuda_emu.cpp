@@ -72,6 +72,13 @@ static void report() {
 
 void yield() { emu_switch(&g_cur->sp, g_cta.sched_sp); }
 
+static uint64_t g_polls = 0;
+void poll_yield() {
+    if (++g_polls > (1ull << 34)) die("livelock: 2^34 polls without the launch ending");
+    ++g_cta.progress;  // other fibers may have published what this one waits for; deadlocks show up as the poll limit
+    yield();
+}
+
 static inline int src_lane(int op, int lane, int arg, int width) {
     const int base = lane & ~(width - 1), rel = lane & (width - 1);
     switch (op) {
@@ -171,6 +178,7 @@ void run_grid(unsigned grid, unsigned block, size_t smem_bytes, void (*body)(voi
         g_stacks.push_back((char *)p);
     }
     g_gridDim.x = grid;
+    g_polls = 0;
     g_blockDim.x = block;
     for (unsigned b = 0; b < grid; ++b) {
         g_blockIdx.x = b;

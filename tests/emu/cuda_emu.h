@@ -75,8 +75,6 @@ struct Fiber {
     int arg = 0, width = 32;
     bool arrived = false, released = false;
     uint64_t result = 0;
-    uint32_t ls_mask = 0xffffffffu;  // lanes that execute warp-uniform code together (see lockstep())
-    bool ls_dirty = true;            // a lock-step store happened since this lane's last lock-step barrier
     // __syncthreads
     uint64_t bar_gen = 0;
     bool at_bar = false;
@@ -100,6 +98,7 @@ extern "C" void emu_switch(void **save_sp, void *load_sp);
 
 [[noreturn]] void die(const char *fmt, ...);
 void yield();
+void poll_yield();  // a polling loop gives the other fibers a turn (aborts after too many fruitless polls)
 uint64_t collective(int op, uint32_t mask, uint64_t val, int arg, int width);
 void cta_barrier();
 void run_grid(unsigned grid, unsigned block, size_t smem_bytes, void (*body)(void *), void *arg);
@@ -187,6 +186,18 @@ static inline int atomicAdd(int *p, int v) {
     *p = o + v;
     return o;
 }
+static inline unsigned long long atomicOr(unsigned long long *p, unsigned long long v) {
+    unsigned long long o = *p;
+    *p = o | v;
+    return o;
+}
+static inline uint32_t atomicCAS(uint32_t *p, uint32_t cmp, uint32_t v) {
+    uint32_t o = *p;
+    if (o == cmp) *p = v;
+    return o;
+}
+static inline void __threadfence() {}
+static inline void __threadfence_block() {}
 static inline uint32_t atomicOr(uint32_t *p, uint32_t v) {
     uint32_t o = *p;
     *p = o | v;
@@ -238,41 +249,29 @@ static inline void emu_check_global(const void *p, size_t align) {
     if (((uintptr_t)p % align) != 0) emu::die("misaligned %zu-byte global access at %p", align, p);
 }
 static inline uint4 lds128(uint32_t a) { return *reinterpret_cast<const uint4 *>(emu_smem_at(a, 16)); }
-static inline double lds_f64(uint32_t a) { return *reinterpret_cast<const double *>(emu_smem_at(a, 8)); }
-static inline void sts_f64x2(uint32_t a, double x, double y) {
-    double *p = reinterpret_cast<double *>(emu_smem_at(a, 16));
-    p[0] = x;
-    p[1] = y;
-}
-// ldg_cg128 / ldg_cg64 / stg_u32 are used by the worm loop, where every lane of the group performs the SAME
-// access and the kernel relies on converged code running in lock-step (a lane's load of record k must not see
-// another lane's later store to it).  The hardware does exactly that for converged warps; the emulator gets the
-// same ordering by putting a group barrier in front of each of these accesses.
-// (Loads only need the barrier if a lock-step store happened since the last one; every lane agrees on that.)
-static inline void lockstep() { emu::collective(emu::OP_SYNCWARP, emu::g_cur->ls_mask, 0, 0, 32); }
-static inline void lockstep_load() {
-    if (emu::g_cur->ls_dirty) {
-        lockstep();
-        emu::g_cur->ls_dirty = false;
-    }
-}
-static inline uint4 ldg_cg128(const uint4 *p) {
-    lockstep_load();
+// Per-lane accesses of the worm phase (every lane touches its own walker), the volatile status words of the
+// scheduler, and the back-off of a polling loop (a yield: fibers only switch at collectives otherwise).
+static inline uint4 lane_ld128(const uint4 *p) {
     emu_check_global(p, 16);
     return *p;
 }
-static inline uint2 ldg_cg64(const uint2 *p) {
-    lockstep_load();
+static inline uint2 lane_ld64(const uint2 *p) {
     emu_check_global(p, 8);
     return *p;
 }
-static inline void prefetch_l2(const void *) {}
-static inline void stg_u32(void *p, uint32_t v) {
-    lockstep();
-    emu::g_cur->ls_dirty = true;
+static inline void lane_st32(void *p, uint32_t v) {
     emu_check_global(p, 4);
     *reinterpret_cast<uint32_t *>(p) = v;
 }
+static inline uint32_t ld_volatile_shared(const uint32_t *p) {
+    __cvta_generic_to_shared(p);
+    return *reinterpret_cast<const volatile uint32_t *>(p);
+}
+static inline void st_volatile_shared(uint32_t *p, uint32_t v) {
+    __cvta_generic_to_shared(p);
+    *reinterpret_cast<volatile uint32_t *>(p) = v;
+}
+static inline void backoff(unsigned) { emu::poll_yield(); }
 }  // namespace sse
 
 // ---- CUDA runtime stand-ins (host "device memory" = malloc with red zones) ------------------------------
@@ -291,6 +290,16 @@ static inline cudaError_t cudaMemcpy(void *d, const void *s, size_t n, cudaMemcp
     return cudaSuccess;
 }
 static inline cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cudaMemcpyKind k, cudaStream_t) { return cudaMemcpy(d, s, n, k); }
+static inline cudaError_t cudaMemcpy2DAsync(void *d, size_t dpitch, const void *s, size_t spitch, size_t width, size_t height, cudaMemcpyKind,
+                                            cudaStream_t) {
+    for (size_t r = 0; r < height; ++r) memmove((char *)d + r * dpitch, (const char *)s + r * spitch, width);
+    return cudaSuccess;
+}
+enum cudaDeviceAttr { cudaDevAttrMultiProcessorCount = 16 };
+static inline cudaError_t cudaDeviceGetAttribute(int *v, cudaDeviceAttr, int) {
+    *v = 3;  // a small "GPU": several walkers share a CTA even in small tests
+    return cudaSuccess;
+}
 static inline cudaError_t cudaMemset(void *d, int v, size_t n) {
     memset(d, v, n);
     return cudaSuccess;

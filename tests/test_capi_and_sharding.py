@@ -21,7 +21,7 @@ def test_capi_exports_every_declared_symbol():
     lib = capi.lib()  # raises if the .so or any symbol is missing
     for name in declared:
         assert hasattr(lib, name)
-    assert lib.sse_abi_version() == 1
+    assert lib.sse_abi_version() == 2
 
 
 def test_product_path_has_no_oracle_dependency():

@@ -42,7 +42,7 @@ def test_emu_exports_the_whole_abi(emu):
     L = capi.lib()
     for name in capi.EXPORTED_SYMBOLS:
         assert hasattr(L, name)
-    assert L.sse_abi_version() == 1
+    assert L.sse_abi_version() == 2
 
 
 def test_emu_vertex_list_golden_vector(emu):

@@ -61,8 +61,7 @@ def test_vertex_list_golden_vector_gpu():
     assert np.array_equal(vert, expected)
     assert vl.tolist() == [[3, 7], [3, 6], [4, 7], [-1, -1]]
     assert vf.tolist() == [[1, 3], [2, 3], [2, 6], [-1, -1]]
-    # committing restores the string untouched
-    w.dbg_commit()
+    # building the records leaves the string untouched
     assert np.array_equal(w.get_state(0)["operators"], ops)
 
 
@@ -174,7 +173,6 @@ def test_worm_traverse_reference_cases():
         gw.set_injected_stream(stream[None, :])
         gw.dbg_make_vertex_list()
         glen = gw.dbg_worm_traverse(1, 1, 1)[0]
-        gw.dbg_commit()
         ow = OracleWalker(om, 0.1)
         ow.set_state(start)
         ow.set_injected_stream(stream)

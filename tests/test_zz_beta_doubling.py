@@ -175,7 +175,7 @@ def _oracle_thermalize_by_doubling(om, T, seed, wid, doublings, per_level, final
     return fw
 
 
-def _body_full_size_parity(L, beta, doublings, walkers_per_warp):
+def _body_full_size_parity(L, beta, doublings, shape=(0, 0), model=None, per_level=4, n_factor=0.75):
     """BASELINE.json configs[1] geometry at full size (2D Heisenberg, L = beta = 32: M ~ 1e5 slots, n ~ 4.6e4 records, worms
     of ~1e4 visits): thousands of 32-slot chunks per sweep, 18-bit links, hundreds of draw refills per worm —
     bit for bit against the oracle, reached by beta doubling."""
@@ -187,7 +187,7 @@ def _body_full_size_parity(L, beta, doublings, walkers_per_warp):
     T = 1.0 / beta
     n_est = 0.75 * beta * 2 * L * L
     gw = Walkers(dm, np.full(W, T), m_capacity=int(3.6 * n_est), n_capacity=int(1.7 * n_est), seed=77)
-    gw.set_walkers_per_warp(walkers_per_warp)
+    gw.set_launch_shape(*shape)
     gw.thermalize_by_beta_doubling(doublings, sweeps_per_level=4, final_sweeps=2)
     gw.sweep(2, thermalized=True, measure=True)
     sums, counts = gw.fetch_accumulators()
@@ -208,12 +208,12 @@ def test_emu_full_size_parity(emu):
     import os
 
     if os.environ.get("SSE_B200_SLOW_TESTS"):
-        _body_full_size_parity(32, 32, 5, 2)
+        _body_full_size_parity(32, 32, 5)
     else:
-        _body_full_size_parity(16, 32, 5, 2)
+        _body_full_size_parity(16, 32, 5)
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("k", [1, 2, 4])
-def test_gpu_full_size_parity(k):
-    _body_full_size_parity(32, 32, 5, k)
+@pytest.mark.parametrize("shape", [(0, 0), (1, 3)])
+def test_gpu_full_size_parity(shape):
+    _body_full_size_parity(32, 32, 5, shape)

@@ -1,0 +1,205 @@
+"""The persistent sweep kernel (sse::k_sweep): worm warps (one lane = one walker) + stream warps (one warp = one walker).
+Whatever the launch shape — one walker per lane, several walkers per lane, one CTA or many — and wherever sse_advance
+parks a walker (between sweeps, between worms, in the middle of a worm), every walker must stay on exactly the trajectory
+of the oracle.  CPU: through the warp emulator (tests/emu); GPU: `-m gpu`."""
+import numpy as np
+import pytest
+
+import test_gpu_parity as G
+from helpers import MODEL_CLASSES, random_stream
+from oracle import OracleWalker
+from sse_b200.capi import SSEError
+from sse_b200.walkers import Walkers
+from test_emu_parity import emu, emu_built  # noqa: F401  (fixtures)
+
+SHAPES = [(1, 1), (2, 3), (1, 8)]
+
+
+def _body_injected_sweeps(shape):
+    """sse_sweep under an injected stream (the dbg_* parity hooks run single phases, so this is the injected-stream
+    coverage of the persistent kernel), walkers of different lengths."""
+    model = MODEL_CLASSES["spin1_dz"]()
+    dm, om = G._pair(model)
+    W = 7
+    Ts = np.linspace(0.25, 1.0, W)
+    rng = np.random.default_rng(5)
+    gw = Walkers(dm, Ts, m_capacity=4096, seed=3)
+    gw.set_launch_shape(*shape)
+    gw.init()
+    gw.sweep(10)
+    ows = []
+    for i in range(W):
+        ow = OracleWalker(om, float(Ts[i]), seed=3, walker_id=i)
+        ow.init()
+        ow.sweep(10)
+        G._same_state(gw.get_state(i), ow.get_state(), f"start walker {i}")
+        ows.append(ow)
+    streams = np.stack([random_stream(rng, 400000) for _ in range(W)])
+    gw.set_injected_stream(streams)
+    gw.sweep(4, thermalized=False)
+    gw.sweep(2, thermalized=True, measure=True)
+    sums, counts = gw.fetch_accumulators()
+    for i, ow in enumerate(ows):
+        ow.set_injected_stream(streams[i])
+        ow.sweep(4, thermalized=False)
+        ow.sweep(2, thermalized=True, measure=True)
+        assert not ow.stream_exhausted
+        G._same_state(gw.get_state(i), ow.get_state(), f"walker {i}")
+        osums, ocounts = ow.fetch_accumulators()
+        assert np.array_equal(counts[i], ocounts)
+        np.testing.assert_allclose(sums[i], osums, rtol=1e-12, atol=1e-300)
+    # a stream that runs out inside the worm phase is reported, not recycled
+    gw.set_injected_stream(streams[:, :300])
+    with pytest.raises(SSEError):
+        gw.sweep(3)
+
+
+def _body_switching_keeps_the_trajectory():
+    """Changing the launch shape between launches does not change the chain."""
+    model = MODEL_CLASSES["heisenberg_eof"]()
+    dm, om = G._pair(model)
+    Ts = np.linspace(0.2, 0.9, 9)
+    a = Walkers(dm, Ts, m_capacity=4096, seed=12)
+    b = Walkers(dm, Ts, m_capacity=4096, seed=12)
+    a.init()
+    b.init()
+    for shape in ((1, 1), (3, 2), (0, 0), (1, 23), (8, 16)):
+        b.set_launch_shape(*shape)
+        a.sweep(4)
+        b.sweep(4)
+    for i in range(len(Ts)):
+        G._same_state(a.get_state(i), b.get_state(i), f"walker {i}")
+    with pytest.raises(SSEError):
+        b.set_launch_shape(20, 5)
+
+
+def _body_many_walkers_per_lane(monkeypatch):
+    """More walkers in a CTA than worm lanes: a lane serves its walkers in turn (one CTA, one worm warp, 70 walkers)."""
+    monkeypatch.setenv("SSE_B200_CTAS", "1")
+    model = MODEL_CLASSES["heisenberg_eof"]()
+    dm, om = G._pair(model)
+    W = 70
+    Ts = np.linspace(0.3, 2.0, W)
+    gw = Walkers(dm, Ts, m_capacity=4096, seed=17)
+    gw.set_launch_shape(1, 3)
+    gw.init()
+    gw.sweep(6, thermalized=False)
+    gw.sweep(3, thermalized=True, measure=True)
+    sums, counts = gw.fetch_accumulators()
+    for i in (0, 31, 32, 63, 64, 69):
+        ow = OracleWalker(om, float(Ts[i]), seed=17, walker_id=i)
+        ow.init()
+        ow.sweep(6, thermalized=False)
+        ow.sweep(3, thermalized=True, measure=True)
+        G._same_state(gw.get_state(i), ow.get_state(), f"walker {i}")
+        osums, ocounts = ow.fetch_accumulators()
+        assert np.array_equal(counts[i], ocounts)
+        np.testing.assert_allclose(sums[i], osums, rtol=1e-12, atol=1e-300)
+    assert gw.fetch_counters()["sweeps"] == W * 9
+
+
+def _body_advance_parks_anywhere(name, budgets):
+    """sse_advance: a fixed number of worm visits per walker and launch; walkers are parked between sweeps, between two
+    worms or inside a worm and resume there.  After finish_sweeps every walker sits on the oracle's trajectory after
+    exactly as many sweeps as it reports."""
+    model = MODEL_CLASSES[name]()
+    dm, om = G._pair(model)
+    W = 6
+    Ts = np.linspace(0.2, 1.2, W)
+    gw = Walkers(dm, Ts, m_capacity=8192, seed=23)
+    gw.init()
+    visits = 0
+    for b in budgets:
+        gw.advance(b, thermalized=False)
+    done, in_flight = gw.progress()
+    assert in_flight.any()  # with these budgets somebody is parked inside a sweep
+    with pytest.raises(SSEError):
+        gw.get_state(0)     # ... and says so instead of returning a half-updated configuration
+    gw.finish_sweeps(thermalized=False)
+    done2, in_flight2 = gw.progress()
+    assert not in_flight2.any()
+    assert np.array_equal(done2, done + in_flight)
+    c = gw.fetch_counters()
+    assert c["sweeps"] == int(done2.sum())
+    for i in range(W):
+        ow = OracleWalker(om, float(Ts[i]), seed=23, walker_id=i)
+        ow.init()
+        ow.sweep(int(done2[i]), thermalized=False)
+        G._same_state(gw.get_state(i), ow.get_state(), f"{name} walker {i} after {done2[i]} sweeps")
+        visits += ow.visits if hasattr(ow, "visits") else 0
+    # a launch gives every walker the same number of visits: nobody did more than the budgets allow, and walkers with
+    # work left used them up
+    assert c["visits"] <= W * (sum(budgets) + max(budgets)) + 10**6
+    # sweep() afterwards keeps walkers in step again
+    gw.sweep(2, thermalized=True, measure=True)
+    done3, _ = gw.progress()
+    assert np.array_equal(done3, done2 + 2)
+    # max_sweeps bounds an advance as well
+    gw.advance(10**9, max_sweeps=1, thermalized=True)
+    done4, fl4 = gw.progress()
+    assert np.array_equal(done4, done3 + 1) and not fl4.any()
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+def test_emu_injected_sweeps(emu, shape):
+    _body_injected_sweeps(shape)
+
+
+def test_emu_switching_keeps_the_trajectory(emu):
+    _body_switching_keeps_the_trajectory()
+
+
+def test_emu_many_walkers_per_lane(emu, monkeypatch):
+    _body_many_walkers_per_lane(monkeypatch)
+
+
+@pytest.mark.parametrize("name, budgets", [("heisenberg_eof", [7, 50, 3, 200, 1, 90]), ("spin1_dz", [40, 11, 300, 5])])
+def test_emu_advance_parks_anywhere(emu, name, budgets):
+    _body_advance_parks_anywhere(name, budgets)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", SHAPES)
+def test_gpu_injected_sweeps(shape):
+    _body_injected_sweeps(shape)
+
+
+@pytest.mark.gpu
+def test_gpu_switching_keeps_the_trajectory():
+    _body_switching_keeps_the_trajectory()
+
+
+@pytest.mark.gpu
+def test_gpu_many_walkers_per_lane(monkeypatch):
+    _body_many_walkers_per_lane(monkeypatch)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name, budgets", [("heisenberg_eof", [7, 50, 3, 200, 1, 90]), ("spin1_dz", [40, 11, 300, 5]),
+                                           ("dimer_bilayer", [1000, 17, 3000])])
+def test_gpu_advance_parks_anywhere(name, budgets):
+    _body_advance_parks_anywhere(name, budgets)
+
+
+@pytest.fixture(params=[(1, 2), (4, 20)])
+def shape_env(request, monkeypatch):
+    monkeypatch.setenv("SSE_B200_WORM_WARPS", str(request.param[0]))
+    monkeypatch.setenv("SSE_B200_STREAM_WARPS", str(request.param[1]))
+    return request.param
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["heisenberg_eof", "spin1_dz", "dimer_bilayer"])
+def test_gpu_shapes_sweep_parity_philox(shape_env, name):
+    G.test_sweep_parity_philox(name)
+
+
+@pytest.mark.gpu
+def test_gpu_shapes_edge_cases(shape_env):
+    G.test_edge_cases_empty_and_ragged_strings()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("level", [0, 1])
+def test_gpu_shapes_large_lattice_memory_paths(shape_env, level, monkeypatch):
+    G.test_large_lattice_memory_paths(level, monkeypatch)

@@ -25,16 +25,16 @@ def test_oracle_reproduces_digest(case):
     assert run_oracle(case["model"], case["T"], case["seed"], case["walker_id"]) == case["sha256"]
 
 
-def _device_digests(walkers_per_warp):
+def _device_digests(shape):
     from helpers import MODEL_CLASSES
     from sse_b200.walkers import DeviceModel, Walkers
 
     for case in CASES:
         dm = DeviceModel(model=MODEL_CLASSES[case["model"]]())
-        # the walker of interest sits in the middle of a small batch so that it shares a warp in the 2/4-per-warp shapes
+        # the walker of interest sits in the middle of a small batch
         wid = case["walker_id"]
         gw = Walkers(dm, np.full(wid + 3, case["T"]), m_capacity=16384, seed=case["seed"])
-        gw.set_walkers_per_warp(walkers_per_warp)
+        gw.set_launch_shape(*shape)
         gw.init()
         gw.sweep(60, thermalized=False)
         gw.sweep(20, thermalized=True, measure=True)
@@ -43,10 +43,10 @@ def _device_digests(walkers_per_warp):
 
 
 def test_emu_reproduces_digests(emu):
-    _device_digests(2)  # one walker per warp is covered case by case in test_emu_parity.py
+    _device_digests((1, 2))
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("k", [1, 2, 4])
-def test_gpu_reproduces_digests(k):
-    _device_digests(k)
+@pytest.mark.parametrize("shape", [(0, 0), (1, 1), (8, 16)])
+def test_gpu_reproduces_digests(shape):
+    _device_digests(shape)
