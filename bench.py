@@ -3,10 +3,13 @@
 
 Metric (BASELINE.json / SURVEY.md §8d): worm operator-vertex visits per second = sum of the lengths
 returned by worm_traverse! (src/sse.jl:302) over all walkers and sweeps / time of the WHOLE sweep.
-Workload at every N: BASELINE.json configs[1], 2D square-lattice S=1/2 Heisenberg AFM L=32, beta=32,
-4096 walkers per GPU (weak scaling: walkers shard over ranks, no data-path collective).
+Workload at every N (default): BASELINE.json configs[2], 2D square-lattice S=1/2 Heisenberg AFM L=64, beta=64,
+as many walkers per GPU as its memory holds (weak scaling: walkers shard over ranks, no data-path collective).
+`--L 32 --beta 32 --walkers 4096` is configs[1]; a short run of it is reported as `secondary` in the same line.
 
-A "step" is one persistent launch advancing every walker by --sweeps-per-step full sweeps.
+A "step" is one persistent launch (sse_advance) in which EVERY walker does `--visits-per-step` worm visits together with
+all the diagonal updates, record builds and measurements of the sweeps it passes through; walkers are parked wherever
+their budget ends and resume there in the next step, so every step is the same amount of work.
 
   python bench.py --gpus 1 --steps K --warmup W            (our arm)
   torchrun ... bench.py --gpus N ...                        (one rank per GPU, NCCL only for bin reduction)
@@ -14,6 +17,7 @@ A "step" is one persistent launch advancing every walker by --sweeps-per-step fu
 """
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -30,36 +34,39 @@ import numpy as np  # noqa: E402
 METRIC = "operator-vertex visits/sec"
 UNIT = "visits/s"
 
+# profiles/r2_chase_lanes.txt (B200, profiles/tools/chase2.cu): dependent 16-byte ld.global.cg + 4-byte st.global per hop,
+# one chain per lane, chains in flight -> hops/s.  The ceiling of a visit that costs nothing but its load and its store.
+CHASE_POINTS = [(4736, 5.98e9), (9472, 1.05e10), (18944, 1.67e10), (37888, 1.99e10), (75776, 2.03e10)]
 
-def build_params(args, n_walkers, walker_id_offset=0, device=-1):
+
+def chain_ceiling(chains):
+    xs = [math.log(c) for c, _ in CHASE_POINTS]
+    ys = [v for _, v in CHASE_POINTS]
+    if chains <= CHASE_POINTS[0][0]:
+        return ys[0] * chains / CHASE_POINTS[0][0]
+    return float(np.interp(math.log(chains), xs, ys))
+
+
+def capacities(L, beta):
+    n_bonds = 2 * L * L
+    n_est = 0.71 * beta * n_bonds  # <n> ~ beta * N_b * (|e_bond| + offset) for the energy_offset_factor = 0.25 tables
+    return int(4.0 * n_est) + 16384, int(1.08 * n_est) + 4096
+
+
+def model_params(args):
     import sse_b200 as S
 
-    L = args.L
-    T = 1.0 / args.beta
-    n_bonds = 2 * L * L
-    # expected n ~ beta * N_b * (|e_bond| + offset) ~ 0.71 * beta * N_b for the eof=0.25 tables
-    n_est = 0.75 * args.beta * n_bonds
-    m_cap = int(args.m_capacity or 3.6 * n_est)
-    n_cap = int(args.n_capacity or 1.7 * n_est)
-    return dict(
-        model=S.MagnetModel,
-        lattice=dict(unitcell=S.UnitCells.square, size=(L, L)),
-        J=1.0,
-        s_half_deterministic=bool(args.deterministic),
-        measure=["magnetization", "staggered_magnetization"],
-        T=T,
-        n_walkers=n_walkers,
-        seed=args.seed,
-        walker_id_offset=walker_id_offset,
-        device=device,
-        m_capacity=m_cap,
-        n_capacity=n_cap,
-    )
+    return dict(model=S.MagnetModel, lattice=dict(unitcell=S.UnitCells.square, size=(args.L, args.L)), J=1.0,
+                s_half_deterministic=bool(args.deterministic), measure=["magnetization", "staggered_magnetization"])
 
 
-def workload_name(args):
+def config_block(args):
     cfg = {(32, 32.0): "BASELINE.json configs[1]", (64, 64.0): "BASELINE.json configs[2]"}.get((args.L, args.beta), "custom size")
-    return f"2D square-lattice S=1/2 Heisenberg AFM L={args.L}, beta={args.beta}, {args.walkers} walkers per GPU ({cfg})"
+    return {
+        "workload": f"2D square-lattice S=1/2 Heisenberg AFM L={args.L}, beta={args.beta}, independent walkers ({cfg})",
+        "energy_offset_factor": 0.0 if args.deterministic else 0.25,
+        "thermalisation": f"beta doubling x{args.beta_doublings} ({args.therm_per_level} sweeps per level) + {args.therm} sweeps at the target",
+    }
 
 
 def measured_peak():
@@ -124,15 +131,14 @@ class ClockSampler:
                 "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def measured_traffic_per_walker_sweep():
-    """DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) per walker-sweep from the committed ncu --set full
-    capture of this kernel on this workload (profiles/r1_d_dram_traffic.json); None if absent."""
+def committed_profile():
+    """Per-visit figures of sse::k_sweep from the committed ncu --set full capture (profiles/r2_ksweep_ncu.json):
+    DRAM bytes and warp-instructions; None if absent."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r1_d_dram_traffic.json")) as f:
-            d = json.load(f)
-        return float(d["dram_bytes_per_walker_sweep"]), d["source"]
+        with open(os.path.join(ROOT, "profiles", "r2_ksweep_ncu.json")) as f:
+            return json.load(f)
     except Exception:
-        return None, None
+        return None
 
 
 def algorithmic_bytes(sum_M, sum_n, visits, measured_sweeps=0):
@@ -140,22 +146,23 @@ def algorithmic_bytes(sum_M, sum_n, visits, measured_sweeps=0):
     return 8.0 * sum_M + 4.0 * sum_M + 16.0 * sum_n + 64.0 * visits + 4.0 * measured_sweeps
 
 
-def cpu_baseline(args, cores=None, therm=None, sweeps=None):
+def cpu_baseline(args, cores=None, sweeps=None, native=True):
     """The CPU oracle (reference data layout, xoshiro256++ stream) on the host cores: one independent walker
-    per thread, as Carlo runs one MC per MPI rank (docs/src/tutorial.md:49)."""
+    per thread, as Carlo runs one MC per MPI rank (docs/src/tutorial.md:49); brought to the target temperature the
+    same way as the device walkers (beta doubling + thermalisation sweeps)."""
     import sse_b200  # noqa: F401
-    from oracle import OracleModel
     import oracle as oracle_mod
+    from oracle import OracleModel
 
     oracle_mod.build()
-    p = build_params(args, 1)
-    model = p["model"](p)
-    om = OracleModel(model)
+    is_native = bool(native and oracle_mod.use_native_build())
+    model = model_params(args)
+    om = OracleModel(model["model"](model))
     cores = cores or os.cpu_count() or 1
-    therm = args.cpu_therm if therm is None else therm
     sweeps = args.cpu_sweeps if sweeps is None else sweeps
-    r = om.bench(p["T"], cores, therm, sweeps, seed=args.seed)
-    return r, cores, therm, sweeps
+    r = om.bench(1.0 / args.beta, cores, args.cpu_therm, sweeps, seed=args.seed, doublings=args.beta_doublings,
+                 per_level=args.therm_per_level)
+    return r, cores, sweeps, is_native
 
 
 def run_reference(args):
@@ -163,17 +170,18 @@ def run_reference(args):
     if rank != 0:
         return
     s = args.cpu_sweeps_per_step
-    r, cores, therm, sweeps = cpu_baseline(args, therm=args.cpu_therm + args.warmup * s, sweeps=args.steps * s)
+    r, cores, sweeps, native = cpu_baseline(args, sweeps=(args.steps + args.warmup) * s)
     value = r["visits"] / r["seconds"]
-    sample = (f"{cores} independent walkers (one per host thread), {therm} thermalisation sweeps untimed, then "
-              f"{sweeps} timed sweeps each = {args.steps} steps x {s} sweeps; mean n={r['mean_n']:.0f}, M={r['mean_M']:.0f}")
+    sample = (f"{cores} independent walkers (one per host thread), thermalised like the device walkers, then "
+              f"{sweeps} timed sweeps each = ({args.steps} steps + {args.warmup} warm-up) x {s} sweeps; mean n={r['mean_n']:.0f}, "
+              f"M={r['mean_M']:.0f}; C++ oracle, reference data layout, xoshiro256++, -O3 {'-march=native' if native else '-march=x86-64-v3'}")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * r["seconds"] / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "u64/f64", "data": "synthetic",
-        "config": {"workload": workload_name(args), "note": "reference CPU path = C++ oracle restating src/sse.jl "
-                   "(julia is not installed in this image); per-walker data layout of the reference",
-                   "energy_offset_factor": 0.0 if args.deterministic else 0.25},
+        "warmup": args.warmup, "ms_per_step": 1e3 * r["seconds"] * args.steps / (args.steps + args.warmup) / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64/f64", "data": "synthetic",
+        "config": config_block(args),
+        "detail": {"note": "reference CPU path = C++ oracle restating src/sse.jl (julia is not installed in this image); "
+                           "per-walker data layout of the reference", "per_core": r["visits"] / r["thread_seconds"]},
         "sweeps_per_s": r["walker_sweeps"] / r["seconds"],
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -185,6 +193,42 @@ def run_reference(args):
 class _DevArr:
     def __init__(self, ptr, shape, typestr):
         self.__cuda_array_interface__ = dict(shape=shape, typestr=typestr, data=(ptr, False), version=2)
+
+
+def setup_walkers(args, dev_index, rank, n_walkers, stream):
+    """Model, walkers, thermalisation (untimed).  Returns (walkers, dmodel, T, setup seconds)."""
+    from sse_b200.walkers import DeviceModel, Walkers
+
+    t0 = time.time()
+    mp = model_params(args)
+    dm = DeviceModel(model=mp["model"](mp))
+    m_cap, n_cap = capacities(args.L, args.beta)
+    if args.m_capacity:
+        m_cap = args.m_capacity
+    if args.n_capacity:
+        n_cap = args.n_capacity
+    W = n_walkers
+    if W <= 0:  # as many as the GPU's memory holds
+        import torch
+
+        free, _total = torch.cuda.mem_get_info(dev_index)
+        per = dm.walker_bytes(m_cap, n_cap)
+        W = int((free - (2 << 30)) * 0.98 / per)
+        W -= W % 148
+        if args.max_walkers:
+            W = min(W, args.max_walkers)
+    T = 1.0 / args.beta
+    wk = Walkers(dm, np.full(W, T), m_capacity=m_cap, n_capacity=n_cap, seed=args.seed, walker_id_offset=rank * W, device=dev_index)
+    wk.set_stream(stream)
+    if args.worm_warps or args.stream_warps:
+        wk.set_launch_shape(args.worm_warps, args.stream_warps)
+    if args.beta_doublings > 0:
+        wk.thermalize_by_beta_doubling(args.beta_doublings, sweeps_per_level=args.therm_per_level)
+    else:
+        wk.init()
+    if args.therm:
+        wk.sweep(args.therm, thermalized=False)
+    return wk, dm, T, W, time.time() - t0
 
 
 def run_ours(args):
@@ -201,18 +245,9 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    from sse_b200.mc import MC
-
-    W = args.walkers
-    S = args.sweeps_per_step
-    params = build_params(args, W, walker_id_offset=rank * W, device=local_rank)
-    t_setup = time.time()
-    mc = MC(params)
-    wk = mc.walkers
     stream = torch.cuda.Stream(device=dev)
-    wk.set_stream(stream.cuda_stream)
-    if args.walkers_per_warp != 1:
-        wk.set_walkers_per_warp(args.walkers_per_warp)
+    wk, dm, T, W, t_setup = setup_walkers(args, local_rank, rank, args.walkers, stream.cuda_stream)
+    B = int(args.visits_per_step)
 
     def barrier():
         torch.cuda.synchronize()
@@ -220,20 +255,8 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # thermalise (untimed): init! + un-thermalised sweeps (string growth, worm-count controller)
-    if args.beta_doublings > 0:
-        # large systems: grow the cold walkers from hot ones (sse_double_beta), then thermalise at the target
-        wk.thermalize_by_beta_doubling(args.beta_doublings, sweeps_per_level=args.therm_per_level)
-    else:
-        wk.init()
-    done = 0
-    while done < args.therm:
-        k = min(50, args.therm - done)
-        wk.sweep(k, thermalized=False, measure=False)
-        done += k
-    for _ in range(args.warmup):
-        wk.sweep(S, thermalized=True, measure=False)
-    t_setup = time.time() - t_setup
+    for _ in range(args.warmup):  # the first one also takes the walkers out of step
+        wk.advance(B, thermalized=True)
 
     # ---- timed region 1: kernel-only, state resident in HBM ----
     wk.fetch_counters(reset=True)
@@ -246,7 +269,7 @@ def run_ours(args):
     with torch.cuda.stream(stream):
         events[0].record(stream)
         for k in range(args.steps):
-            wk.sweep(S, thermalized=True, measure=False, sync=False)
+            wk.advance(B, thermalized=True, measure=False, sync=False)
             events[k + 1].record(stream)
     barrier()
     wk.sync()
@@ -257,34 +280,62 @@ def run_ours(args):
 
     # ---- timed region 2: end to end through the public API with host buffers ----
     n_obs = wk.n_obs
-    T_host = torch.full((W,), params["T"], dtype=torch.float64).pin_memory()
+    T_host = torch.full((W,), T, dtype=torch.float64).pin_memory()
     T_np = T_host.numpy()
     sptr, cptr = wk.accumulators_device_ptr()
     acc_t = torch.as_tensor(_DevArr(sptr, (W, n_obs), "<f8"), device=dev)
     barrier()
     t0 = time.perf_counter()
     for k in range(args.steps):
-        wk.set_temperature(T_np)                                  # H2D: this step's parameters
-        wk.sweep(S, thermalized=True, measure=True, sync=False)   # sweeps + on-device estimators
-        if world > 1:                                             # NCCL: reduce the binned observables only
+        wk.set_temperature(T_np)                                     # H2D: this step's parameters
+        wk.advance(B, thermalized=True, measure=True, sync=False)    # sweeps + on-device estimators
+        if world > 1:                                                # NCCL: reduce the binned observables only
             with torch.cuda.stream(stream):
                 bin_sum = acc_t.sum(dim=0)
                 dist.all_reduce(bin_sum)
-        sums, counts = wk.fetch_accumulators(reset=True)          # D2H: the bin
+        sums, counts = wk.fetch_accumulators(reset=True)             # D2H: the bin
     barrier()
     e2e_s = time.perf_counter() - t0
     cnt2 = wk.fetch_counters(reset=True)
-    energy = float(sums[:, 4].sum() / sums[:, 0].sum())
+    have = counts[:, 0] > 0
+    energy = float((sums[have, 4] / counts[have, 0]).mean() / (sums[have, 0] / counts[have, 0]).mean()) if have.any() else None
+
+    # ---- timed region 3: the call pattern of a Carlo job (julia/SSEB200.jl): sweep! = one launch of one sweep + sync,
+    #      measure! = sse_measure with all observables copied to the host; and its batched form (sweeps_per_call) ----
+    carlo = None
+    if args.carlo_steps > 0:
+        wk.finish_sweeps(thermalized=True)
+        wk.fetch_counters(reset=True)
+        barrier()
+        t0 = time.perf_counter()
+        for k in range(args.carlo_steps):
+            wk.sweep(1, thermalized=True, measure=False)
+            wk.measure()
+        barrier()
+        dt1 = time.perf_counter() - t0
+        c1 = wk.fetch_counters(reset=True)
+        S = args.carlo_batch
+        t0 = time.perf_counter()
+        for k in range(max(1, args.carlo_steps // 2)):
+            wk.sweep(S, thermalized=True, measure=True)
+            wk.fetch_accumulators(reset=True)
+        barrier()
+        dt2 = time.perf_counter() - t0
+        c2 = wk.fetch_counters(reset=True)
+        carlo = {"per_sweep_launch": {"value": c1["visits"] / dt1, "unit": UNIT, "api": "sse_sweep(1) + sse_sync + sse_measure per Carlo step",
+                                      "steps": args.carlo_steps, "ms_per_sweep": 1e3 * dt1 / args.carlo_steps},
+                 "batched": {"value": c2["visits"] / dt2, "unit": UNIT, "sweeps_per_call": S,
+                             "api": "sse_sweep(sweeps_per_call, measure=1) + sse_fetch_accumulators per Carlo step"}}
 
     # ---- aggregate over ranks: max time, summed work ----
     red = torch.tensor([ms_total, e2e_s * 1e3], dtype=torch.float64, device=dev)
-    tot = torch.tensor([cnt["visits"], cnt["sweeps"], cnt["sum_n"], cnt["sum_M"], cnt2["visits"], cnt2["sweeps"]],
+    tot = torch.tensor([cnt["visits"], cnt["sweeps"], cnt["sum_n"], cnt["sum_M"], cnt2["visits"], cnt2["sweeps"], W],
                        dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(red, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot)
     ms_total, e2e_ms = red.tolist()
-    visits, sweeps, sum_n, sum_M, visits2, sweeps2 = tot.tolist()
+    visits, sweeps, sum_n, sum_M, visits2, sweeps2, W_all = tot.tolist()
 
     if rank == 0:
         peak, peak_src = measured_peak()
@@ -292,44 +343,63 @@ def run_ours(args):
         b_launch = algorithmic_bytes(cnt["sum_M"], cnt["sum_n"], cnt["visits"]) / args.steps
         avg_launch_ms = float(np.mean(launch_ms))
         achieved = b_launch / (avg_launch_ms * 1e-3) / 1e9
-        tpws, tsrc = measured_traffic_per_walker_sweep()
-        default_workload = (args.L == 32 and args.beta == 32.0 and not args.deterministic)
-        traffic = tpws * cnt["sweeps"] / args.steps if (tpws and default_workload) else None
+        rank_visits_per_s = cnt["visits"] / (ms_total * 1e-3)
+        prof = committed_profile()
+        traffic = issue_frac = None
+        if prof and prof.get("L") == args.L:
+            traffic = prof["dram_bytes_per_visit"] * cnt["visits"] / args.steps
+            issue_frac = prof["warp_instructions_per_visit"] * rank_visits_per_s / (148 * 4 * 1.965e9)
+        occupancy = cnt["lane_iters"] / max(1, 32 * cnt["warp_iters"])
+        clk = (clocks or {}).get("sm_mhz") or 1965.0
+        cfg = config_block(args)
+        cfg.update({
+            "walkers_per_gpu": W, "visits_per_walker_per_step": B, "n_sites": args.L * args.L,
+            "mean_n": sum_n / max(1, sweeps), "mean_M": sum_M / max(1, sweeps), "visits_per_sweep": visits / max(1, sweeps),
+            "l2": "inputs larger than L2: per-GPU walker state %.1f GB >> 126 MB" % (wk.device_bytes() / 1e9),
+            "bytes_per_walker": wk.device_bytes() / W,
+            "parallelism": f"walkers sharded over {world} rank(s), no collective inside a sweep",
+        })
         line = {
             "metric": METRIC, "value": visits / (ms_total * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u32/f64", "data": "synthetic",
-            "config": {
-                "workload": workload_name(args), "walkers_per_gpu": W, "walkers_per_warp": args.walkers_per_warp,
-                "sweeps_per_step": S,
-                "thermalisation_sweeps": args.therm, "beta_doublings": args.beta_doublings, "energy_offset_factor": 0.0 if args.deterministic else 0.25,
-                "mean_n": sum_n / sweeps, "mean_M": sum_M / sweeps, "visits_per_sweep": visits / sweeps,
-                "l2": "inputs larger than L2: per-GPU walker state %.1f GB >> 126 MB" % (wk.device_bytes() / 1e9),
-                "parallelism": f"walkers sharded over {world} rank(s), no collective inside a sweep",
-            },
+            "config": cfg,
             "sweeps_per_s": sweeps / (ms_total * 1e-3),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "traffic_source": tsrc if traffic else None, "peak_source": peak_src,
-                         "kernel": "sse::k_walkers<false>" if args.walkers_per_warp == 1 else "sse::k_walkers_multi<false,%d>" % args.walkers_per_warp,
-                         "avg_launch_ms": avg_launch_ms, "algorithmic_bytes_per_launch": b_launch,
-                         "formula": "12*M + 16*n + 64*V per walker-sweep (SURVEY.md 8d)"},
+                         "traffic": traffic, "traffic_source": (prof or {}).get("source") if traffic else None, "peak_source": peak_src,
+                         "kernel": "sse::k_sweep<false>", "avg_launch_ms": avg_launch_ms, "algorithmic_bytes_per_launch": b_launch,
+                         "formula": "12*M + 16*n + 64*V per walker-sweep (SURVEY.md 8d)",
+                         # the two other ceilings of this latency-bound path
+                         "chain_ceiling": {"value": chain_ceiling(W), "unit": UNIT, "frac": rank_visits_per_s / chain_ceiling(W),
+                                           "what": "hops/s of W dependent 16-byte-load + 4-byte-store chains, one per lane (profiles/r2_chase_lanes.txt)"},
+                         "issue_frac": issue_frac},
             "e2e": {"value": visits2 / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 8 * W,
                     "d2h_bytes_per_step": 8 * W * n_obs + 16 * W, "ms_per_step": e2e_ms / args.steps,
-                    "api": "sse_set_temperature + sse_sweep(measure=1) + sse_fetch_accumulators per step",
+                    "api": "sse_set_temperature + sse_advance(measure=1) + sse_fetch_accumulators per step",
                     "energy_per_site": energy},
+            "carlo_call_pattern": carlo,
             "gpu_launches": args.steps,
-            "phase_cycle_share": {k: cnt[k] / max(1, cnt["cycles_diag_build"] + cnt["cycles_worm"] + cnt["cycles_commit_measure"])
-                                  for k in ("cycles_diag_build", "cycles_worm", "cycles_commit_measure")},
-            "worm_cycles_per_visit": cnt["cycles_worm"] / max(1, cnt["visits"]),
+            "kernel_stats": {
+                "worm_lane_occupancy": occupancy,
+                "worm_loop_ns_per_iteration": cnt["cycles_worm"] / max(1, cnt["warp_iters"]) / clk * 1e3,
+                "stream_warps_busy_per_sm": (cnt["cycles_build"] + cnt["cycles_finish"]) / (ms_total * 1e-3 * clk * 1e6) / min(W, 148),
+                "build_ms_per_walker_sweep": cnt["cycles_build"] / max(1, cnt["sweeps"]) / clk * 1e-3,
+                "finish_ms_per_walker_sweep": cnt["cycles_finish"] / max(1, cnt["sweeps"]) / clk * 1e-3,
+            },
             "clocks": clocks,
             "setup_s": t_setup,
         }
+    del wk
+    if rank == 0:
+        if world == 1 and args.secondary and (args.L, args.beta) == (64, 64.0):
+            line["secondary"] = secondary_config1(args, local_rank, stream)
         if world == 1 and not args.no_cpu:
-            r, cores, therm, sw = cpu_baseline(args)
+            r, cores, sw, native = cpu_baseline(args)
             line["cpu_baseline"] = {
                 "value": r["visits"] / r["seconds"], "unit": UNIT, "cores": cores, "kind": "port",
-                "sample": f"{cores} walkers (one per host thread), {therm} thermalisation + {sw} timed sweeps each, "
-                          f"mean n={r['mean_n']:.0f}; C++ oracle, reference data layout, xoshiro256++",
+                "sample": f"{cores} walkers (one per host thread), thermalised like the device walkers, {sw} timed sweeps each, "
+                          f"mean n={r['mean_n']:.0f}; C++ oracle, reference data layout, xoshiro256++, "
+                          f"{'-march=native' if native else '-march=x86-64-v3'}",
                 "per_core": r["visits"] / r["thread_seconds"],
             }
         print(json.dumps(line))
@@ -338,37 +408,73 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def secondary_config1(args, dev_index, stream):
+    """BASELINE.json configs[1] (L = beta = 32, 4096 walkers on one B200), short run of the same kernel."""
+    import copy
+    import torch
+
+    a = copy.copy(args)
+    a.L, a.beta, a.beta_doublings, a.therm, a.m_capacity, a.n_capacity = 32, 32.0, 5, 20, 0, 0
+    wk, dm, T, W, t_setup = setup_walkers(a, dev_index, 0, 4096, stream.cuda_stream)
+    B = 300000
+    wk.advance(B, thermalized=True)
+    wk.fetch_counters(reset=True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    with torch.cuda.stream(stream):
+        e0.record(stream)
+        for _ in range(3):
+            wk.advance(B, thermalized=True, sync=False)
+        e1.record(stream)
+    torch.cuda.synchronize()
+    wk.sync()
+    c = wk.fetch_counters(reset=True)
+    ms = e0.elapsed_time(e1)
+    return {"config": config_block(a), "walkers_per_gpu": W, "value": c["visits"] / (ms * 1e-3), "unit": UNIT, "steps": 3,
+            "ms_per_step": ms / 3, "sweeps_per_s": c["sweeps"] / (ms * 1e-3), "mean_n": c["sum_n"] / max(1, c["sweeps"]),
+            "chain_ceiling": chain_ceiling(W), "setup_s": t_setup}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--L", type=int, default=32)
-    ap.add_argument("--beta", type=float, default=32.0)
-    ap.add_argument("--walkers", type=int, default=4096, help="walkers per GPU")
-    ap.add_argument("--walkers-per-warp", type=int, default=1, choices=[1, 2, 4],
-                    help="launch shape (sse_set_walkers_per_warp): 2 or 4 interleave the worm updates of a warp's walkers; "
-                         "meant for --walkers well beyond 4144 (e.g. --walkers 8192 --walkers-per-warp 2)")
-    ap.add_argument("--sweeps-per-step", type=int, default=64,
-                    help="sweeps per launch (one Carlo bin; the reference tutorial uses binsize 100). Longer launches "
-                         "average the per-walker worm-length imbalance: busy fraction 81 %% at 32, 86 %% at 100")
-    ap.add_argument("--therm", type=int, default=300)
-    ap.add_argument("--beta-doublings", type=int, default=0,
-                    help="untimed setup: start 2^k times hotter and double beta k times (sse_double_beta) before the "
-                         "--therm sweeps at the target; for L=64, beta=64 use 6")
-    ap.add_argument("--therm-per-level", type=int, default=10,
+    ap.add_argument("--L", type=int, default=64)
+    ap.add_argument("--beta", type=float, default=64.0)
+    ap.add_argument("--walkers", type=int, default=0, help="walkers per GPU; 0 = as many as the GPU's memory holds")
+    ap.add_argument("--max-walkers", type=int, default=0)
+    ap.add_argument("--visits-per-step", type=float, default=1.5e6,
+                    help="worm visits every walker does per step (one sse_advance launch); ~2 sweeps at L = beta = 64")
+    ap.add_argument("--worm-warps", type=int, default=0)
+    ap.add_argument("--stream-warps", type=int, default=0)
+    ap.add_argument("--therm", type=int, default=12, help="sweeps at the target temperature after the doubling levels")
+    ap.add_argument("--beta-doublings", type=int, default=-1,
+                    help="untimed setup: start 2^k times hotter and double beta k times (sse_double_beta); default log2(beta)")
+    ap.add_argument("--therm-per-level", type=int, default=8,
                     help="sweeps per beta-doubling level (run with the controller attenuation 0.1, see Walkers.thermalize_by_beta_doubling)")
     ap.add_argument("--deterministic", action="store_true",
                     help="energy_offset_factor=0 tables (the reference's intended but unreachable S=1/2 branch)")
     ap.add_argument("--seed", type=int, default=20261017)
     ap.add_argument("--m-capacity", type=int, default=0)
     ap.add_argument("--n-capacity", type=int, default=0)
-    ap.add_argument("--cpu-therm", type=int, default=300)
-    ap.add_argument("--cpu-sweeps", type=int, default=400)
-    ap.add_argument("--cpu-sweeps-per-step", type=int, default=80)
+    ap.add_argument("--carlo-steps", type=int, default=2, help="steps of the Carlo call-pattern leg (0 = skip)")
+    ap.add_argument("--carlo-batch", type=int, default=4)
+    ap.add_argument("--no-secondary", dest="secondary", action="store_false")
+    ap.add_argument("--cpu-therm", type=int, default=12)
+    ap.add_argument("--cpu-sweeps", type=int, default=0, help="timed sweeps per host thread of the cpu_baseline leg (0 = ~15 s worth)")
+    ap.add_argument("--cpu-sweeps-per-step", type=int, default=0, help="--impl reference: sweeps per step and thread (0 = ~3 s worth)")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
+    if args.beta_doublings < 0:
+        args.beta_doublings = max(0, int(round(math.log2(args.beta))))
+    # one CPU walker-sweep costs ~ n * 2.1 visits at ~1e7 visits/s
+    sweep_s = 0.71 * args.beta * 2 * args.L * args.L * 2.1 / 1.0e7
+    if args.cpu_sweeps <= 0:
+        args.cpu_sweeps = max(8, int(15.0 / sweep_s))
+    if args.cpu_sweeps_per_step <= 0:
+        args.cpu_sweeps_per_step = max(2, int(3.0 / sweep_s))
     if args.impl == "reference":
         run_reference(args)
     else:

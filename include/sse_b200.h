@@ -125,6 +125,9 @@ int32_t sse_walkers_create(const sse_model *m, const sse_walkers_opts *opts, sse
 int32_t sse_walkers_destroy(sse_walkers *w);
 int32_t sse_set_stream(sse_walkers *w, void *cuda_stream);
 int32_t sse_n_observables(const sse_walkers *w);
+/* Device bytes one walker of `m` costs at these capacities (0.25 B per string slot + 17 B per operator + 9 B per site +
+ * accumulators): for sizing a batch to the GPU's memory. */
+int64_t sse_walker_bytes(const sse_model *m, int64_t m_capacity, int64_t n_capacity);
 int64_t sse_device_bytes(const sse_walkers *w);
 
 /* Carlo.init!(mc, ctx, params) (src/sse.jl:47-60): random state, `init_opstring_cutoff` identities
@@ -199,7 +202,7 @@ int32_t sse_get_num_operators(sse_walkers *w, int64_t *out /* [n_walkers] */);
 /* Launch shape of sse_sweep / sse_advance, NOT in the reference: warps per CTA that chase worms (one lane = one
  * walker) and warps that run the streaming phases (one warp = one walker); one CTA per SM.  0 = choose automatically
  * from the number of walkers (default; environment SSE_B200_WORM_WARPS / SSE_B200_STREAM_WARPS at creation).
- * worm_warps + stream_warps <= 24.  Results do not depend on this setting (bit-identical). */
+ * worm_warps + stream_warps <= 16.  Results do not depend on this setting (bit-identical). */
 int32_t sse_set_launch_shape(sse_walkers *w, int32_t worm_warps, int32_t stream_warps);
 
 /* The two parameters of the worm-count controller (src/sse.jl:34-35,204-217), changeable between launches.

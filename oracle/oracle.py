@@ -24,6 +24,24 @@ def build(force: bool = False):
         subprocess.check_call(["make", "-C", _HERE, "-B" if force else "-s"])
 
 
+def use_native_build() -> bool:
+    """bench.py's CPU legs only: compile the oracle for THIS host's cores (-march=native, still -ffp-contract=off) into
+    oracle/_native/ and load that instead of the portable build (SURVEY.md 8d asks for -march=native; the portable .so
+    that travels with the repo is x86-64-v3).  Must be called before the first lib().  False if the compile fails."""
+    global LIB_PATH, _lib
+    out_dir = os.path.join(_HERE, "_native")
+    out = os.path.join(out_dir, "libsse_oracle.so")
+    try:
+        os.makedirs(out_dir, exist_ok=True)
+        subprocess.check_call(["g++", "-O3", "-march=native", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-pthread",
+                               "-o", out, os.path.join(_HERE, "sse_oracle.cpp")], stderr=subprocess.DEVNULL)
+    except Exception:
+        return False
+    LIB_PATH = out
+    _lib = None
+    return True
+
+
 def lib():
     global _lib
     if _lib is None:
@@ -66,6 +84,7 @@ def lib():
         L.oracle_set_state.argtypes = [vp, C.POINTER(WalkerState)]
         L.oracle_get_vertex_list.argtypes = [vp, i64p, i64p, i64p]
         L.oracle_bench.argtypes = [vp, C.c_double, C.c_int32, C.c_int32, C.c_int32, C.c_uint64, f64p]
+        L.oracle_bench2.argtypes = [vp, C.c_double, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_uint64, f64p]
         _lib = L
     return _lib
 
@@ -83,9 +102,9 @@ class OracleModel:
             lib().oracle_model_destroy(self.handle)
             self.handle = None
 
-    def bench(self, T: float, n_threads: int, therm: int, sweeps: int, seed: int = 1):
+    def bench(self, T: float, n_threads: int, therm: int, sweeps: int, seed: int = 1, doublings: int = 0, per_level: int = 10):
         out = np.zeros(6)
-        lib().oracle_bench(self.handle, T, n_threads, therm, sweeps, seed, out.ctypes.data_as(f64p))
+        lib().oracle_bench2(self.handle, T, n_threads, doublings, per_level, therm, sweeps, seed, out.ctypes.data_as(f64p))
         return dict(seconds=out[0], visits=out[1], walker_sweeps=out[2], mean_n=out[3], mean_M=out[4], thread_seconds=out[5])
 
 

@@ -647,6 +647,53 @@ void oracle_get_vertex_list(void *w, int64_t *vertices, int64_t *v_first, int64_
 // Timed CPU baseline: `n_threads` independent walkers (one per thread, as Carlo runs one MC per MPI rank,
 // docs/src/tutorial.md:49), xoshiro256++ stream, `therm` un-thermalised + `sweeps` timed sweeps each.
 // out = {seconds (max over threads), total visits, total walker-sweeps, mean n, mean M, sum of per-thread seconds}.
+// `doublings` > 0: the walkers are brought to T the way bench.py brings the device walkers there (sse_double_beta restated:
+// init! at T * 2^doublings, `per_level` sweeps and one doubling (state, S_M) -> (state, S_M S_M), n -> 2n, T -> T/2 per level
+// with the controller's attenuation factor at 0.1), then `therm` sweeps at T.  Needed for L = beta = 64, where the
+// reference's cold start takes thousands of sweeps.
+void oracle_bench2(void *model, double T, int32_t n_threads, int32_t doublings, int32_t per_level, int32_t therm, int32_t sweeps,
+                   uint64_t seed, double *out) {
+    SSEData *sd = static_cast<SSEData *>(model);
+    std::vector<double> secs(n_threads, 0.0), visits(n_threads, 0.0), nsum(n_threads, 0.0), msum(n_threads, 0.0);
+    std::atomic<int> ready{0};
+    std::atomic<bool> go{false};
+    auto worker = [&](int t) {
+        MC *mc = new_walker(sd, std::ldexp(T, doublings), 2, seed, uint64_t(t), 2.0, doublings > 0 ? 0.1 : 0.01, 5.0);
+        init(*mc, -1, 5);
+        for (int level = 0; level < doublings; ++level) {
+            for (int i = 0; i < per_level; ++i) sweep(*mc, false, false);
+            const Int M = mc->M();
+            mc->operators.resize(2 * M + 1);
+            std::copy(mc->operators.begin() + 1, mc->operators.begin() + 1 + M, mc->operators.begin() + 1 + M);
+            mc->num_operators *= 2;
+            mc->T *= 0.5;
+            mc->avg_worm_length *= 2.0;
+        }
+        mc->num_worms_attenuation_factor = 0.01;
+        for (int i = 0; i < therm; ++i) sweep(*mc, false, false);
+        for (int i = 0; i < 4; ++i) mc->counters[i] = 0;
+        ready.fetch_add(1);
+        while (!go.load()) std::this_thread::yield();
+        auto t0 = std::chrono::steady_clock::now();
+        for (int i = 0; i < sweeps; ++i) sweep(*mc, true, false);
+        auto t1 = std::chrono::steady_clock::now();
+        secs[t] = std::chrono::duration<double>(t1 - t0).count();
+        visits[t] = double(mc->counters[0]);
+        nsum[t] = double(mc->counters[2]);
+        msum[t] = double(mc->counters[3]);
+        delete mc;
+    };
+    std::vector<std::thread> th;
+    for (int t = 0; t < n_threads; ++t) th.emplace_back(worker, t);
+    while (ready.load() < n_threads) std::this_thread::yield();
+    go.store(true);
+    for (auto &x : th) x.join();
+    double smax = 0, ssum = 0, v = 0, ns = 0, ms = 0;
+    for (int t = 0; t < n_threads; ++t) { smax = std::max(smax, secs[t]); ssum += secs[t]; v += visits[t]; ns += nsum[t]; ms += msum[t]; }
+    out[0] = smax; out[1] = v; out[2] = double(n_threads) * sweeps;
+    out[3] = ns / (double(n_threads) * sweeps); out[4] = ms / (double(n_threads) * sweeps); out[5] = ssum;
+}
+
 void oracle_bench(void *model, double T, int32_t n_threads, int32_t therm, int32_t sweeps, uint64_t seed, double *out) {
     SSEData *sd = static_cast<SSEData *>(model);
     std::vector<double> secs(n_threads, 0.0), visits(n_threads, 0.0), nsum(n_threads, 0.0), msum(n_threads, 0.0);

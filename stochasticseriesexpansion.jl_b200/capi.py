@@ -137,6 +137,7 @@ def lib():
         "sse_set_stream": (C.c_int32, [vp, vp]),
         "sse_n_observables": (C.c_int32, [vp]),
         "sse_device_bytes": (C.c_int64, [vp]),
+        "sse_walker_bytes": (C.c_int64, [vp, C.c_int64, C.c_int64]),
         "sse_init": (C.c_int32, [vp, C.c_int64, C.c_int32]),
         "sse_sweep": (C.c_int32, [vp, C.c_int32, C.c_int32, C.c_int32]),
         "sse_sync": (C.c_int32, [vp]),
@@ -174,7 +175,7 @@ def lib():
 
 EXPORTED_SYMBOLS = [
     "sse_last_error", "sse_abi_version", "sse_model_create", "sse_model_destroy", "sse_walkers_create",
-    "sse_walkers_destroy", "sse_set_stream", "sse_n_observables", "sse_device_bytes", "sse_init", "sse_sweep",
+    "sse_walkers_destroy", "sse_set_stream", "sse_n_observables", "sse_device_bytes", "sse_walker_bytes", "sse_init", "sse_sweep",
     "sse_sync", "sse_measure", "sse_fetch_accumulators", "sse_accumulators_device_ptr", "sse_fetch_counters",
     "sse_get_state", "sse_set_state", "sse_get_flags", "sse_pt_log_weight_ratio", "sse_set_temperature",
     "sse_get_num_operators", "sse_double_beta", "sse_set_controller", "sse_set_launch_shape",

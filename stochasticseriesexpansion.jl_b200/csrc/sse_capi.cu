@@ -156,7 +156,7 @@ int32_t sweep_shape(const sse_walkers *w, SweepShape &sh) {
     sh.nloc_max = (W + sh.grid - 1) / sh.grid;
     int ww = w->worm_warps > 0 ? w->worm_warps : std::min(8, (sh.nloc_max + 31) / 32);
     int sw = w->stream_warps > 0 ? w->stream_warps : std::min(SWEEP_MAX_WARPS - ww, std::max(1, std::min(16, sh.nloc_max)));
-    if (ww < 1 || sw < 1 || ww + sw > SWEEP_MAX_WARPS) return fail("launch shape: need 1 <= worm_warps, 1 <= stream_warps, worm_warps + stream_warps <= 24");
+    if (ww < 1 || sw < 1 || ww + sw > SWEEP_MAX_WARPS) return fail("launch shape: need 1 <= worm_warps, 1 <= stream_warps, worm_warps + stream_warps <= 16");
     const int budget = 227 * 1024 - 1024;
     const int fixed = m->dm.tl.bytes + sched_bytes(sh.nloc_max);
     sh.level = 1;
@@ -480,6 +480,16 @@ int32_t sse_set_stream(sse_walkers *w, void *cuda_stream) {
     if (w->own_stream) { cudaStreamDestroy(w->stream); w->own_stream = false; }
     w->stream = (cudaStream_t)cuda_stream;
     return 0;
+}
+
+int64_t sse_walker_bytes(const sse_model *m, int64_t m_capacity, int64_t n_capacity) {
+    if (!m || m_capacity < 0 || n_capacity < 0) return -1;
+    const int64_t N = m->dm.n_sites, n_obs = SSE_OBS_FIXED + SSE_OBS_PER_ESTIMATOR * m->dm.n_est;
+    int64_t b = ((m_capacity + 31) / 32) * (int64_t)sizeof(uint2) + ring_size(n_capacity) * (int64_t)sizeof(uint4);
+    b += N * (1 + 4 + 4) + (int64_t)sizeof(WalkerCtl) + n_obs * 8 * 2 + 16 + 8;
+    const int fixed = m->dm.tl.bytes + sched_bytes(1024);
+    if ((227 * 1024 - 1024 - fixed) / stream_scratch_bytes((int)N, 1) < 4 || !phase_level(m)) b += N;  // global mark[] scratch
+    return b;
 }
 
 int32_t sse_n_observables(const sse_walkers *w) { return w ? w->dw.n_obs : -1; }

@@ -45,7 +45,7 @@ constexpr uint32_t VMASK = ((1u << VBITS) - 1u) << 2;  // bits 2..13
 constexpr int BOND_SHIFT = 2 + VBITS;                  // 14
 constexpr int RNG_WORDS = 66;                          // 33 Philox blocks x 2 draws (see phase_diag_build)
 constexpr int PHASE_WARPS = 4;                         // warps per CTA of sse::k_phase (one warp = one walker)
-constexpr int SWEEP_MAX_WARPS = 24;                    // warps per CTA of sse::k_sweep (launch bounds 768 x 1)
+constexpr int SWEEP_MAX_WARPS = 16;                    // warps per CTA of sse::k_sweep (launch bounds 512 x 1: 128 registers per thread)
 constexpr int ROT_MARGIN = 64;                         // ring slack kept between the write head and unread old records
 
 __host__ __device__ __forceinline__ uint32_t op_pack(uint32_t bond, uint32_t gv, uint32_t diag) {

@@ -95,6 +95,143 @@ __device__ uint32_t stream_task(const SmTab &st, const DevModel &dm, const DevWa
     return next;
 }
 
+// Role of a worm warp inside k_sweep: one lane = one walker (walkers j = lane index + m * lanes of the CTA's status table).
+template <bool INJ>
+__device__ __forceinline__ void worm_warp_role(const SmTab &st, const DevModel &dm, const DevWalkers &dw, const SweepArgs &a, uint32_t *n_done,
+                                            uint32_t *status, int nloc, int warp, uint32_t lane) {
+    // ------------------------------ worm warp: one lane = one walker ------------------------------
+    const LaneEnv env = lane_env(st, dm, dw);
+    const int nlanes = a.worm_warps * 32, me = warp * 32 + (int)lane;
+    int cur = -1;
+    bool finished = me >= nloc;
+    WormLane L;
+    unsigned long long visits = 0, it_active = 0, it_total = 0;
+    const long long t_begin = clock64();
+    while (true) {
+        if (cur < 0 && !finished) {
+            bool all_done = true;
+            for (int j = me; j < nloc; j += nlanes) {
+                const uint32_t s = ld_volatile_shared(status + j);
+                if (s == WS_READY_WORM) { cur = j; break; }
+                if (s != WS_DONE) all_done = false;
+            }
+            if (cur >= 0) {
+                __threadfence();  // the stream warp's writes (records, words, control block) are visible
+                st_volatile_shared(status + cur, WS_IN_WORM);
+                const int w = (int)blockIdx.x + cur * (int)gridDim.x;
+                lane_open(dw, w, L);
+                bool ok = true;
+                if (__ldcg(&dw.ctl[w].inworm)) lane_resume(env, L);
+                else ok = lane_pick_start<INJ>(env, L);
+                if (!ok) {  // injected stream exhausted
+                    lane_store(dw, w, L, 0, SSE_FLAG_STREAM_EXHAUSTED);
+                    __threadfence();
+                    st_volatile_shared(status + cur, WS_DONE);
+                    atomicAdd(n_done, 1u);
+                    cur = -1;
+                }
+            } else if (all_done) {
+                finished = true;
+            }
+        }
+        if (cur >= 0) {
+            ++it_active;
+            const int w = (int)blockIdx.x + cur * (int)gridDim.x;
+            const bool closed = lane_visit<INJ>(env, L);
+            if (L.budget_left != ~0ull) --L.budget_left;
+            uint32_t post = 0xffffffffu, inworm = 0, extra = 0;
+            if (INJ && (long long)L.draws > env.inj_len) {
+                extra = SSE_FLAG_STREAM_EXHAUSTED;
+                post = WS_DONE;
+                if (closed) { L.sweep_visits += L.len; visits += L.len; }
+            } else if (closed) {
+                L.sweep_visits += L.len;  // total_worm_length += worm_traverse!(...) (sse.jl:197)
+                visits += L.len;
+                if (--L.worms_left == 0) post = WS_NEED_STREAM;
+                else if (L.budget_left == 0) post = WS_DONE;
+                else if (!lane_pick_start<INJ>(env, L)) { extra = SSE_FLAG_STREAM_EXHAUSTED; post = WS_DONE; }
+            } else if (L.budget_left == 0) {
+                post = WS_DONE;  // park in the middle of the worm
+                inworm = 1;
+            }
+            if (post != 0xffffffffu) {
+                lane_store(dw, w, L, inworm, extra);
+                __threadfence();  // op-code stores and the control block before the hand-over
+                st_volatile_shared(status + cur, post);
+                if (post == WS_DONE) atomicAdd(n_done, 1u);
+                cur = -1;
+            }
+        }
+        ++it_total;
+        const uint32_t fin = __ballot_sync(FULL, finished);
+        if (fin == FULL) break;
+        if (!__ballot_sync(FULL, cur >= 0)) backoff(256);
+    }
+    const unsigned long long cyc = (unsigned long long)(clock64() - t_begin);
+    visits = warp_sum_u64(visits);
+    it_active = warp_sum_u64(it_active);
+    if (lane == 0) {
+        if (visits) atomicAdd(dw.counters + SSE_CNT_VISITS, visits);
+        atomicAdd(dw.counters + SSE_CNT_CYC_WORM, cyc);
+        atomicAdd(dw.counters + SSE_CNT_LANE_ITERS, it_active);
+        atomicAdd(dw.counters + SSE_CNT_WARP_ITERS, it_total);
+    }
+}
+
+// Role of a stream warp inside k_sweep: claim walkers that wait for streaming until every walker of the CTA is done.
+template <bool INJ>
+__device__ __forceinline__ void stream_warp_role(const SmTab &st, const DevModel &dm, const DevWalkers &dw, const SweepArgs &a, uint32_t *n_done,
+                                              uint32_t *status, int nloc, uint8_t *scratch, uint32_t lane) {
+    // ------------------------------ stream warp: one warp = one walker ------------------------------
+    SweepStats ss = {0, 0, 0, 0, 0, 0, 0, 0};
+    while (true) {
+        // claim a walker that waits for streaming: lanes scan the status table, the lowest hit is tried first
+        int j = -1;
+        const long long t0 = clock64();
+        for (int b = 0; b < nloc && j < 0; b += 32) {
+            const int jj = b + (int)lane;
+            const bool want = jj < nloc && ld_volatile_shared(status + jj) == WS_NEED_STREAM;
+            uint32_t m = __ballot_sync(FULL, want);
+            while (m && j < 0) {
+                const int t = __ffs(m) - 1;
+                m &= m - 1;
+                uint32_t got = 0;
+                if ((int)lane == t) got = atomicCAS(status + jj, (uint32_t)WS_NEED_STREAM, (uint32_t)WS_STREAMING) == WS_NEED_STREAM;
+                got = __shfl_sync(FULL, got, t);
+                if (got) j = b + t;
+            }
+        }
+        if (j < 0) {
+            // one lane decides for the warp (lanes reading the counter at different times would disagree)
+            if (__shfl_sync(FULL, ld_volatile_shared(n_done), 0) >= (uint32_t)nloc) break;
+            backoff(512);
+            ss.cyc_idle += (unsigned long long)(clock64() - t0);
+            continue;
+        }
+        __threadfence();  // the worm lane's writes (op codes, control block) are visible
+        const int w = (int)blockIdx.x + j * (int)gridDim.x;
+        const uint32_t next = stream_task<INJ>(st, dm, dw, a, w, scratch, lane, ss);
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) {
+            st_volatile_shared(status + j, next);
+            if (next == WS_DONE) atomicAdd(n_done, 1u);
+        }
+        __syncwarp();
+    }
+    if (lane == 0) {
+        if (ss.sweeps) {
+            atomicAdd(dw.counters + SSE_CNT_SWEEPS, ss.sweeps);
+            atomicAdd(dw.counters + SSE_CNT_SUM_N, ss.sum_n);
+            atomicAdd(dw.counters + SSE_CNT_SUM_M, ss.sum_M);
+        }
+        atomicAdd(dw.counters + SSE_CNT_CYC_BUILD, ss.cyc_build);
+        atomicAdd(dw.counters + SSE_CNT_CYC_FINISH, ss.cyc_finish);
+        atomicAdd(dw.counters + SSE_CNT_CYC_IDLE, ss.cyc_idle);
+        atomicAdd(dw.counters + SSE_CNT_TASKS, ss.tasks);
+    }
+}
+
 template <bool INJ>
 __global__ void __launch_bounds__(SWEEP_MAX_WARPS * 32, 1) k_sweep(const DevModel dm, const DevWalkers dw, const SweepArgs a) {
     extern __shared__ __align__(16) uint8_t smem[];
@@ -126,134 +263,11 @@ __global__ void __launch_bounds__(SWEEP_MAX_WARPS * 32, 1) k_sweep(const DevMode
     __syncthreads();
 
     if (warp < a.worm_warps) {
-        // ------------------------------ worm warp: one lane = one walker ------------------------------
-        const LaneEnv env = lane_env(st, dm, dw);
-        const int nlanes = a.worm_warps * 32, me = warp * 32 + (int)lane;
-        int cur = -1;
-        bool finished = me >= nloc;
-        WormLane L;
-        unsigned long long visits = 0, it_active = 0, it_total = 0;
-        const long long t_begin = clock64();
-        while (true) {
-            if (cur < 0 && !finished) {
-                bool all_done = true;
-                for (int j = me; j < nloc; j += nlanes) {
-                    const uint32_t s = ld_volatile_shared(status + j);
-                    if (s == WS_READY_WORM) { cur = j; break; }
-                    if (s != WS_DONE) all_done = false;
-                }
-                if (cur >= 0) {
-                    __threadfence();  // the stream warp's writes (records, words, control block) are visible
-                    st_volatile_shared(status + cur, WS_IN_WORM);
-                    const int w = (int)blockIdx.x + cur * (int)gridDim.x;
-                    lane_open(dw, w, L);
-                    bool ok = true;
-                    if (__ldcg(&dw.ctl[w].inworm)) lane_resume(env, L);
-                    else ok = lane_pick_start<INJ>(env, L);
-                    if (!ok) {  // injected stream exhausted
-                        lane_store(dw, w, L, 0, SSE_FLAG_STREAM_EXHAUSTED);
-                        __threadfence();
-                        st_volatile_shared(status + cur, WS_DONE);
-                        atomicAdd(n_done, 1u);
-                        cur = -1;
-                    }
-                } else if (all_done) {
-                    finished = true;
-                }
-            }
-            if (cur >= 0) {
-                ++it_active;
-                const int w = (int)blockIdx.x + cur * (int)gridDim.x;
-                const bool closed = lane_visit<INJ>(env, L);
-                if (L.budget_left != ~0ull) --L.budget_left;
-                uint32_t post = 0xffffffffu, inworm = 0, extra = 0;
-                if (INJ && (long long)L.draws > env.inj_len) {
-                    extra = SSE_FLAG_STREAM_EXHAUSTED;
-                    post = WS_DONE;
-                    if (closed) { L.sweep_visits += L.len; visits += L.len; }
-                } else if (closed) {
-                    L.sweep_visits += L.len;  // total_worm_length += worm_traverse!(...) (sse.jl:197)
-                    visits += L.len;
-                    if (--L.worms_left == 0) post = WS_NEED_STREAM;
-                    else if (L.budget_left == 0) post = WS_DONE;
-                    else if (!lane_pick_start<INJ>(env, L)) { extra = SSE_FLAG_STREAM_EXHAUSTED; post = WS_DONE; }
-                } else if (L.budget_left == 0) {
-                    post = WS_DONE;  // park in the middle of the worm
-                    inworm = 1;
-                }
-                if (post != 0xffffffffu) {
-                    lane_store(dw, w, L, inworm, extra);
-                    __threadfence();  // op-code stores and the control block before the hand-over
-                    st_volatile_shared(status + cur, post);
-                    if (post == WS_DONE) atomicAdd(n_done, 1u);
-                    cur = -1;
-                }
-            }
-            ++it_total;
-            const uint32_t fin = __ballot_sync(FULL, finished);
-            if (fin == FULL) break;
-            if (!__ballot_sync(FULL, cur >= 0)) backoff(256);
-        }
-        const unsigned long long cyc = (unsigned long long)(clock64() - t_begin);
-        visits = warp_sum_u64(visits);
-        it_active = warp_sum_u64(it_active);
-        if (lane == 0) {
-            if (visits) atomicAdd(dw.counters + SSE_CNT_VISITS, visits);
-            atomicAdd(dw.counters + SSE_CNT_CYC_WORM, cyc);
-            atomicAdd(dw.counters + SSE_CNT_LANE_ITERS, it_active);
-            atomicAdd(dw.counters + SSE_CNT_WARP_ITERS, it_total);
-        }
+        worm_warp_role<INJ>(st, dm, dw, a, n_done, status, nloc, warp, lane);
     } else if (warp < a.worm_warps + a.stream_warps) {
-        // ------------------------------ stream warp: one warp = one walker ------------------------------
         uint8_t *scratch = smem + dm.tl.bytes + sched_bytes(a.nloc_max) +
                            (size_t)(warp - a.worm_warps) * stream_scratch_bytes(dm.n_sites, a.level);
-        SweepStats ss = {0, 0, 0, 0, 0, 0, 0, 0};
-        while (true) {
-            // claim a walker that waits for streaming: lanes scan the status table, the lowest hit is tried first
-            int j = -1;
-            const long long t0 = clock64();
-            for (int b = 0; b < nloc && j < 0; b += 32) {
-                const int jj = b + (int)lane;
-                const bool want = jj < nloc && ld_volatile_shared(status + jj) == WS_NEED_STREAM;
-                uint32_t m = __ballot_sync(FULL, want);
-                while (m && j < 0) {
-                    const int t = __ffs(m) - 1;
-                    m &= m - 1;
-                    uint32_t got = 0;
-                    if ((int)lane == t) got = atomicCAS(status + jj, (uint32_t)WS_NEED_STREAM, (uint32_t)WS_STREAMING) == WS_NEED_STREAM;
-                    got = __shfl_sync(FULL, got, t);
-                    if (got) j = b + t;
-                }
-            }
-            if (j < 0) {
-                // one lane decides for the warp (lanes reading the counter at different times would disagree)
-                if (__shfl_sync(FULL, ld_volatile_shared(n_done), 0) >= (uint32_t)nloc) break;
-                backoff(512);
-                ss.cyc_idle += (unsigned long long)(clock64() - t0);
-                continue;
-            }
-            __threadfence();  // the worm lane's writes (op codes, control block) are visible
-            const int w = (int)blockIdx.x + j * (int)gridDim.x;
-            const uint32_t next = stream_task<INJ>(st, dm, dw, a, w, scratch, lane, ss);
-            __threadfence();
-            __syncwarp();
-            if (lane == 0) {
-                st_volatile_shared(status + j, next);
-                if (next == WS_DONE) atomicAdd(n_done, 1u);
-            }
-            __syncwarp();
-        }
-        if (lane == 0) {
-            if (ss.sweeps) {
-                atomicAdd(dw.counters + SSE_CNT_SWEEPS, ss.sweeps);
-                atomicAdd(dw.counters + SSE_CNT_SUM_N, ss.sum_n);
-                atomicAdd(dw.counters + SSE_CNT_SUM_M, ss.sum_M);
-            }
-            atomicAdd(dw.counters + SSE_CNT_CYC_BUILD, ss.cyc_build);
-            atomicAdd(dw.counters + SSE_CNT_CYC_FINISH, ss.cyc_finish);
-            atomicAdd(dw.counters + SSE_CNT_CYC_IDLE, ss.cyc_idle);
-            atomicAdd(dw.counters + SSE_CNT_TASKS, ss.tasks);
-        }
+        stream_warp_role<INJ>(st, dm, dw, a, n_done, status, nloc, scratch, lane);
     }
 }
 

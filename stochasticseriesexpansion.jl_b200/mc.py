@@ -35,7 +35,7 @@ def default_capacity(sse_data, T_min: float):
     cannot exceed: M <= 3 n + 100 in the worst case, n <= the spectral bound (+ fluctuations)."""
     nb = operator_count_bound(sse_data, T_min)
     nb = nb + 8.0 * np.sqrt(nb) + 64
-    return int(3.0 * nb + 1124), int(min(nb + 256, 1 << 22))
+    return int(3.0 * nb + 1124), int(min(nb + 256, (1 << 22) - 1))
 
 
 class MC:

@@ -30,6 +30,10 @@ class DeviceModel:
         self.L = capi.lib()
         check(self.L.sse_model_create(C.byref(desc), C.byref(self.handle)))
 
+    def walker_bytes(self, m_capacity: int, n_capacity: int) -> int:
+        """Device bytes per walker at these capacities (for sizing a batch to the GPU's memory)."""
+        return int(self.L.sse_walker_bytes(self.handle, int(m_capacity), int(n_capacity)))
+
     def observable_names(self):
         names = list(OBS_FIXED)
         ests = self.model.get_opstring_estimators() if self.model is not None else []
@@ -64,7 +68,7 @@ class Walkers:
         o.n_walkers = self.n_walkers
         o.T = self.T.ctypes.data_as(f64p)
         o.m_capacity = int(m_capacity)
-        o.n_capacity = int(n_capacity if n_capacity is not None else min(m_capacity, 1 << 22))
+        o.n_capacity = int(n_capacity if n_capacity is not None else min(m_capacity, (1 << 22) - 1))
         o.device = device
         o.seed = seed
         o.walker_id_offset = walker_id_offset

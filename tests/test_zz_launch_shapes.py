@@ -63,14 +63,14 @@ def _body_switching_keeps_the_trajectory():
     b = Walkers(dm, Ts, m_capacity=4096, seed=12)
     a.init()
     b.init()
-    for shape in ((1, 1), (3, 2), (0, 0), (1, 23), (8, 16)):
+    for shape in ((1, 1), (3, 2), (0, 0), (1, 15), (8, 8)):
         b.set_launch_shape(*shape)
         a.sweep(4)
         b.sweep(4)
     for i in range(len(Ts)):
         G._same_state(a.get_state(i), b.get_state(i), f"walker {i}")
     with pytest.raises(SSEError):
-        b.set_launch_shape(20, 5)
+        b.set_launch_shape(12, 5)
 
 
 def _body_many_walkers_per_lane(monkeypatch):
@@ -181,7 +181,7 @@ def test_gpu_advance_parks_anywhere(name, budgets):
     _body_advance_parks_anywhere(name, budgets)
 
 
-@pytest.fixture(params=[(1, 2), (4, 20)])
+@pytest.fixture(params=[(1, 2), (4, 12)])
 def shape_env(request, monkeypatch):
     monkeypatch.setenv("SSE_B200_WORM_WARPS", str(request.param[0]))
     monkeypatch.setenv("SSE_B200_STREAM_WARPS", str(request.param[1]))

@@ -47,6 +47,6 @@ def test_emu_reproduces_digests(emu):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("shape", [(0, 0), (1, 1), (8, 16)])
+@pytest.mark.parametrize("shape", [(0, 0), (1, 1), (8, 8)])
 def test_gpu_reproduces_digests(shape):
     _device_digests(shape)
