@@ -190,11 +190,6 @@ def run_reference(args):
     print(json.dumps(line))
 
 
-class _DevArr:
-    def __init__(self, ptr, shape, typestr):
-        self.__cuda_array_interface__ = dict(shape=shape, typestr=typestr, data=(ptr, False), version=2)
-
-
 def setup_walkers(args, dev_index, rank, n_walkers, stream):
     """Model, walkers, thermalisation (untimed).  Returns (walkers, dmodel, T, setup seconds)."""
     from sse_b200.walkers import DeviceModel, Walkers
@@ -245,6 +240,8 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
+    from sse_b200.walkers import Walkers
+
     stream = torch.cuda.Stream(device=dev)
     wk, dm, T, W, t_setup = setup_walkers(args, local_rank, rank, args.walkers, stream.cuda_stream)
     B = int(args.visits_per_step)
@@ -282,23 +279,21 @@ def run_ours(args):
     n_obs = wk.n_obs
     T_host = torch.full((W,), T, dtype=torch.float64).pin_memory()
     T_np = T_host.numpy()
-    sptr, cptr = wk.accumulators_device_ptr()
-    acc_t = torch.as_tensor(_DevArr(sptr, (W, n_obs), "<f8"), device=dev)
+    if world > 1:  # the library's own NCCL communicator (sse_comm_init): the id travels over torch.distributed
+        box = [Walkers.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        wk.comm_init(box[0], rank, world)
     barrier()
     t0 = time.perf_counter()
     for k in range(args.steps):
         wk.set_temperature(T_np)                                     # H2D: this step's parameters
         wk.advance(B, thermalized=True, measure=True, sync=False)    # sweeps + on-device estimators
-        if world > 1:                                                # NCCL: reduce the binned observables only
-            with torch.cuda.stream(stream):
-                bin_sum = acc_t.sum(dim=0)
-                dist.all_reduce(bin_sum)
-        sums, counts = wk.fetch_accumulators(reset=True)             # D2H: the bin
+        sums, counts = wk.reduce_bins(None, 1, reset=True)           # the bin: summed over walkers on the device, over
+                                                                     # ranks by NCCL inside the library, then D2H
     barrier()
     e2e_s = time.perf_counter() - t0
     cnt2 = wk.fetch_counters(reset=True)
-    have = counts[:, 0] > 0
-    energy = float((sums[have, 4] / counts[have, 0]).mean() / (sums[have, 0] / counts[have, 0]).mean()) if have.any() else None
+    energy = float(sums[0, 4] / sums[0, 0]) if counts[0, 0] > 0 else None
 
     # ---- timed region 3: the call pattern of a Carlo job (julia/SSEB200.jl): sweep! = one launch of one sweep + sync,
     #      measure! = sse_measure with all observables copied to the host; and its batched form (sweeps_per_call) ----
@@ -374,8 +369,9 @@ def run_ours(args):
                                            "what": "hops/s of W dependent 16-byte-load + 4-byte-store chains, one per lane (profiles/r2_chase_lanes.txt)"},
                          "issue_frac": issue_frac},
             "e2e": {"value": visits2 / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 8 * W,
-                    "d2h_bytes_per_step": 8 * W * n_obs + 16 * W, "ms_per_step": e2e_ms / args.steps,
-                    "api": "sse_set_temperature + sse_advance(measure=1) + sse_fetch_accumulators per step",
+                    "d2h_bytes_per_step": 8 * (n_obs + 2), "ms_per_step": e2e_ms / args.steps,
+                    "api": "sse_set_temperature + sse_advance(measure=1) + sse_reduce_bins (device sum over walkers, NCCL all-reduce "
+                           "over ranks inside the library) per step",
                     "energy_per_site": energy},
             "carlo_call_pattern": carlo,
             "gpu_launches": args.steps,

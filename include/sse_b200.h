@@ -164,7 +164,17 @@ int32_t sse_measure(sse_walkers *w, double *out);
 /* Per-walker sums accumulated by sse_sweep(measure=1): sums[n_walkers][n_obs], counts[n_walkers][2]
  * (measurements, WormLengthFraction measurements).  reset != 0 zeroes them afterwards (one "bin"). */
 int32_t sse_fetch_accumulators(sse_walkers *w, double *sums, int64_t *counts, int32_t reset);
-/* Device pointers of the same buffers, for NCCL reductions by the host (no copy). */
+/* One bin reduced inside the library: the accumulators of the walkers of each group (group[i] in
+ * 0..n_groups-1, e.g. the index of the walker's temperature; NULL = one group) are summed on the device in walker
+ * order, all-reduced over the ranks of sse_comm_init with NCCL on the handle's stream (skipped without a communicator),
+ * and returned: sums[n_groups][n_obs], counts[n_groups][2].  Every rank must call it with the same n_groups.
+ * Replaces Carlo's MPI merge of `measure!` accumulators (src/sse.jl:73-83,201; magnetization_estimator.jl:218-227)
+ * for a host without a GPU-aware reduction of its own.  NCCL (libnccl.so.2) is resolved at run time. */
+typedef struct sse_nccl_id { char internal[128]; } sse_nccl_id;   /* = ncclUniqueId */
+int32_t sse_comm_unique_id(sse_nccl_id *id);                       /* rank 0 creates it, the host broadcasts it (MPI, ...) */
+int32_t sse_comm_init(sse_walkers *w, const sse_nccl_id *id, int32_t rank, int32_t nranks);
+int32_t sse_reduce_bins(sse_walkers *w, const int32_t *group, int32_t n_groups, double *sums, int64_t *counts, int32_t reset);
+/* Device pointers of the accumulator buffers, for reductions by a host that has its own collective (no copy). */
 int32_t sse_accumulators_device_ptr(sse_walkers *w, void **sums, void **counts);
 
 /* Totals since creation or the last reset (sse_fetch_counters):
@@ -198,6 +208,19 @@ int32_t sse_get_flags(sse_walkers *w, uint32_t *flags /* [n_walkers] */);
 int32_t sse_pt_log_weight_ratio(sse_walkers *w, const double *new_T, double *out /* [n_walkers] */);
 int32_t sse_set_temperature(sse_walkers *w, const double *T /* [n_walkers] */);
 int32_t sse_get_num_operators(sse_walkers *w, int64_t *out /* [n_walkers] */);
+int32_t sse_get_temperatures(sse_walkers *w, double *T /* [n_walkers] */);
+
+/* Replica exchange decided ON THE DEVICE with the two hooks above (what Carlo's parallel-tempering wrapper does with
+ * them over MPI).  sse_pt_set_ladder names the walkers of a temperature ladder in rank order (walker_at_rank[n]);
+ * sse_pt_exchange proposes the neighbour swaps (rank r, r+1), r = parity, parity+2, ...: pair i is accepted iff
+ * log(u_i) < lw_a + lw_b with lw_x = -n_x * log(T_other / T_x) (src/sse.jl:395) and u_i = draw i of the Philox stream
+ * (seed, step) — sse_pt_uniforms returns the same numbers to a host that wants to replay the decisions.  Accepted
+ * pairs exchange their temperatures (src/sse.jl:398-405) and their places on the ladder; configurations never move.
+ * Needs walkers between sweeps.  n_accepted may be NULL (then the call is asynchronous). */
+int32_t sse_pt_set_ladder(sse_walkers *w, const int32_t *walker_at_rank, int32_t n);
+int32_t sse_pt_get_ladder(sse_walkers *w, int32_t *walker_at_rank);
+int32_t sse_pt_exchange(sse_walkers *w, int32_t parity, uint64_t seed, uint64_t step, int32_t *n_accepted);
+int32_t sse_pt_uniforms(uint64_t seed, uint64_t step, int32_t n, double *out);
 
 /* Launch shape of sse_sweep / sse_advance, NOT in the reference: warps per CTA that chase worms (one lane = one
  * walker) and warps that run the streaming phases (one warp = one walker); one CTA per SM.  0 = choose automatically

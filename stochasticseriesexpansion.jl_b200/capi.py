@@ -145,12 +145,20 @@ def lib():
         "sse_fetch_accumulators": (C.c_int32, [vp, f64p, i64p, C.c_int32]),
         "sse_accumulators_device_ptr": (C.c_int32, [vp, C.POINTER(vp), C.POINTER(vp)]),
         "sse_fetch_counters": (C.c_int32, [vp, u64p, C.c_int32]),
+        "sse_comm_unique_id": (C.c_int32, [C.c_char_p]),
+        "sse_comm_init": (C.c_int32, [vp, C.c_char_p, C.c_int32, C.c_int32]),
+        "sse_reduce_bins": (C.c_int32, [vp, i32p, C.c_int32, f64p, i64p, C.c_int32]),
         "sse_get_state": (C.c_int32, [vp, C.c_int32, C.POINTER(WalkerState)]),
         "sse_set_state": (C.c_int32, [vp, C.c_int32, C.POINTER(WalkerState)]),
         "sse_get_flags": (C.c_int32, [vp, u32p]),
         "sse_pt_log_weight_ratio": (C.c_int32, [vp, f64p, f64p]),
         "sse_set_temperature": (C.c_int32, [vp, f64p]),
         "sse_get_num_operators": (C.c_int32, [vp, i64p]),
+        "sse_get_temperatures": (C.c_int32, [vp, f64p]),
+        "sse_pt_set_ladder": (C.c_int32, [vp, i32p, C.c_int32]),
+        "sse_pt_get_ladder": (C.c_int32, [vp, i32p]),
+        "sse_pt_exchange": (C.c_int32, [vp, C.c_int32, C.c_uint64, C.c_uint64, i32p]),
+        "sse_pt_uniforms": (C.c_int32, [C.c_uint64, C.c_uint64, C.c_int32, f64p]),
         "sse_double_beta": (C.c_int32, [vp]),
         "sse_set_controller": (C.c_int32, [vp, C.c_double, C.c_double]),
         "sse_set_launch_shape": (C.c_int32, [vp, C.c_int32, C.c_int32]),
@@ -177,8 +185,9 @@ EXPORTED_SYMBOLS = [
     "sse_last_error", "sse_abi_version", "sse_model_create", "sse_model_destroy", "sse_walkers_create",
     "sse_walkers_destroy", "sse_set_stream", "sse_n_observables", "sse_device_bytes", "sse_walker_bytes", "sse_init", "sse_sweep",
     "sse_sync", "sse_measure", "sse_fetch_accumulators", "sse_accumulators_device_ptr", "sse_fetch_counters",
+    "sse_comm_unique_id", "sse_comm_init", "sse_reduce_bins",
     "sse_get_state", "sse_set_state", "sse_get_flags", "sse_pt_log_weight_ratio", "sse_set_temperature",
-    "sse_get_num_operators", "sse_double_beta", "sse_set_controller", "sse_set_launch_shape",
+    "sse_get_num_operators", "sse_get_temperatures", "sse_pt_set_ladder", "sse_pt_get_ladder", "sse_pt_exchange", "sse_pt_uniforms", "sse_double_beta", "sse_set_controller", "sse_set_launch_shape",
     "sse_advance", "sse_finish_sweeps", "sse_get_progress",
     "sse_set_injected_stream", "sse_dbg_diagonal_update", "sse_dbg_make_vertex_list",
     "sse_dbg_worm_update", "sse_dbg_worm_traverse", "sse_dbg_get_vertex_list",

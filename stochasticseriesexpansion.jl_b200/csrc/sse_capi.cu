@@ -14,6 +14,10 @@
 
 #include "sse_sweep.cuh"
 
+#ifndef SSE_EMU
+#include <dlfcn.h>
+#endif
+
 using namespace sse;
 
 // Kernel launches go through one macro so that the test-only warp emulator (tests/emu) can compile this file with g++.
@@ -75,6 +79,12 @@ struct sse_walkers {
     unsigned long long *d_inj = nullptr;
     int64_t bytes = 0;
     std::vector<void *> allocs;
+    void *comm = nullptr;                  // ncclComm_t of sse_comm_init (bin reduction only)
+    int comm_rank = 0, comm_nranks = 1;
+    void *d_red = nullptr;                 // staging of sse_reduce_bins
+    size_t red_bytes = 0;
+    int32_t *d_ladder = nullptr;           // sse_pt_set_ladder: walker index at each temperature rank; then the accept counter
+    int n_ladder = 0;
 };
 
 namespace {
@@ -159,14 +169,18 @@ int32_t sweep_shape(const sse_walkers *w, SweepShape &sh) {
     if (ww < 1 || sw < 1 || ww + sw > SWEEP_MAX_WARPS) return fail("launch shape: need 1 <= worm_warps, 1 <= stream_warps, worm_warps + stream_warps <= 16");
     const int budget = 227 * 1024 - 1024;
     const int fixed = m->dm.tl.bytes + sched_bytes(sh.nloc_max);
-    sh.level = 1;
-    if (const char *lv = getenv("SSE_B200_SMEM_LEVEL")) sh.level = std::min(sh.level, std::max(0, atoi(lv)));
-    if (sh.level == 1) {
-        // as many streaming warps with state[] and mark[] in shared memory as fit; below 4, keep them in global memory instead
-        const int per = stream_scratch_bytes(N, 1);
-        const int fit = (budget - fixed) / per;
-        if (fit >= std::min(sw, 4)) sw = std::min(sw, fit);
-        else sh.level = 0;
+    // stream warps keep state[] and mark[] (level 1) and vlast[] (level 2) of their walker in shared memory: level 2 if at
+    // least 8 warps (or all that were asked for) fit, else level 1 if at least 4 fit, else everything stays in global memory
+    int max_level = 2;
+    if (const char *lv = getenv("SSE_B200_SMEM_LEVEL")) max_level = std::min(max_level, std::max(0, atoi(lv)));
+    sh.level = 0;
+    for (int level = max_level; level >= 1; --level) {
+        const int fit = (budget - fixed) / stream_scratch_bytes(N, level);
+        if (fit >= std::min(sw, level == 2 ? 8 : 4)) {
+            sh.level = level;
+            sw = std::min(sw, fit);
+            break;
+        }
     }
     if (!sh.level && !w->dw.mark) return fail("internal: mark[] scratch missing");
     sh.worm_warps = ww;
@@ -225,6 +239,86 @@ int32_t require_between_sweeps(sse_walkers *w, const char *who) {
         if (ph[i]) return fail(std::string(who) + ": walker " + std::to_string(i) + " is parked inside a sweep (sse_advance); call sse_finish_sweeps first");
     w->maybe_in_flight = false;
     return 0;
+}
+
+// ---- NCCL, resolved at run time: the library has no link-time dependency on it, and a host that already loaded an NCCL
+// (PyTorch bundles one) shares that copy.  Used for ONE thing: summing binned observables over ranks. ----
+struct NcclApi {
+    bool ok = false;
+    std::string why;
+    int (*GetUniqueId)(void *) = nullptr;
+    int (*CommInitRank)(void **, int, sse_nccl_id, int) = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+    int (*CommDestroy)(void *) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+};
+NcclApi &nccl() {
+    static NcclApi api;
+    static bool tried = false;
+    if (tried) return api;
+    tried = true;
+#ifdef SSE_EMU
+    api.why = "NCCL is not available in the emulator build";
+#else
+    void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);  // an NCCL the host process already uses
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) { api.why = std::string("libnccl.so.2 not found: ") + dlerror(); return api; }
+    api.GetUniqueId = (int (*)(void *))dlsym(h, "ncclGetUniqueId");
+    api.CommInitRank = (int (*)(void **, int, sse_nccl_id, int))dlsym(h, "ncclCommInitRank");
+    api.AllReduce = (int (*)(const void *, void *, size_t, int, int, void *, cudaStream_t))dlsym(h, "ncclAllReduce");
+    api.CommDestroy = (int (*)(void *))dlsym(h, "ncclCommDestroy");
+    api.GetErrorString = (const char *(*)(int))dlsym(h, "ncclGetErrorString");
+    api.ok = api.GetUniqueId && api.CommInitRank && api.AllReduce && api.CommDestroy && api.GetErrorString;
+    if (!api.ok) api.why = "libnccl.so.2 lacks an expected symbol";
+#endif
+    return api;
+}
+#define NC(call)                                                                                         \
+    do {                                                                                                 \
+        int r__ = (call);                                                                                \
+        if (r__ != 0) return fail(std::string(#call) + " failed: " + nccl().GetErrorString(r__));        \
+    } while (0)
+
+// Per-group sums of the walkers' accumulators in a FIXED order (walker order inside each group), so a bin is
+// reproducible bit for bit: thread (g, i) adds column i of the walkers listed for group g.
+// out[g][n_obs + 2]: n_obs sums, then the two counts (as doubles: exact below 2^53).
+__global__ void k_reduce_bins(const DevWalkers dw, const int32_t *start, const int32_t *members, int n_groups, double *out) {
+    const int ncol = dw.n_obs + 2;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_groups * ncol) return;
+    const int g = t / ncol, i = t % ncol;
+    double s = 0.0;
+    for (int k = start[g]; k < start[g + 1]; ++k) {
+        const int w = members[k];
+        s += i < dw.n_obs ? dw.acc[(size_t)w * dw.n_obs + i] : (double)dw.acc_cnt[2 * w + (i - dw.n_obs)];
+    }
+    out[t] = s;
+}
+
+// One round of neighbour swaps on the temperature ladder (parallel tempering, src/sse.jl:390-405): thread i proposes to
+// exchange the temperatures of the walkers at ranks r = parity + 2i and r + 1 and accepts with
+// min(1, exp(lw_a + lw_b)), lw_x = parallel_tempering_log_weight_ratio(x, :T, T_other) = -n_x * log(T_other / T_x)
+// (sse.jl:395).  The uniform is draw i of the Philox stream (seed, step): the walkers' own streams are not touched.
+// Configurations never move, only the temperature labels (parallel_tempering_change_parameter!, sse.jl:398-405).
+__global__ void k_pt_exchange(const DevWalkers dw, int32_t *ladder, int n_ladder, int parity, unsigned long long seed,
+                              unsigned long long step, int32_t *n_accepted) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = parity + 2 * i;
+    if (r + 1 >= n_ladder) return;
+    const int a = ladder[r], b = ladder[r + 1];
+    WalkerCtl *ca = dw.ctl + a, *cb = dw.ctl + b;
+    if ((ca->flags | cb->flags) & FATAL_FLAGS) return;
+    const double Ta = ca->T, Tb = cb->T;
+    const double lw = -(double)ca->n * log(Tb / Ta) + -(double)cb->n * log(Ta / Tb);
+    const double u = sse_u01(sse_philox_draw(seed, step, (unsigned long long)i));
+    if (log(u > 1e-300 ? u : 1e-300) < lw) {
+        ca->T = Tb;
+        cb->T = Ta;
+        ladder[r] = b;
+        ladder[r + 1] = a;
+        atomicAdd(n_accepted, 1);
+    }
 }
 
 int64_t ring_size(int64_t n_cap) { return n_cap + std::max<int64_t>(2048, n_cap / 16); }
@@ -469,6 +563,9 @@ int32_t sse_walkers_destroy(sse_walkers *w) {
     if (w->stream) cudaStreamSynchronize(w->stream);
     for (void *p : w->allocs) cudaFree(p);
     if (w->d_inj) cudaFree(w->d_inj);
+    if (w->d_red) cudaFree(w->d_red);
+    if (w->d_ladder) cudaFree(w->d_ladder);
+    if (w->comm && nccl().ok) nccl().CommDestroy(w->comm);
     if (w->own_stream && w->stream) cudaStreamDestroy(w->stream);
     delete w;
     return 0;
@@ -601,6 +698,75 @@ int32_t sse_accumulators_device_ptr(sse_walkers *w, void **sums, void **counts) 
     if (sums) *sums = w->dw.acc;
     if (counts) *counts = w->dw.acc_cnt;
     return 0;
+}
+
+int32_t sse_comm_unique_id(sse_nccl_id *id) {
+    if (!id) return fail("null argument");
+    if (!nccl().ok) return fail("sse_comm_unique_id: " + nccl().why);
+    NC(nccl().GetUniqueId(id));
+    return 0;
+}
+
+int32_t sse_comm_init(sse_walkers *w, const sse_nccl_id *id, int32_t rank, int32_t nranks) {
+    if (!w || !id) return fail("null argument");
+    if (nranks < 1 || rank < 0 || rank >= nranks) return fail("sse_comm_init: rank out of range");
+    if (!nccl().ok) return fail("sse_comm_init: " + nccl().why);
+    CU(cudaSetDevice(w->model->device));
+    if (w->comm) { nccl().CommDestroy(w->comm); w->comm = nullptr; }
+    NC(nccl().CommInitRank(&w->comm, nranks, *id, rank));
+    w->comm_rank = rank;
+    w->comm_nranks = nranks;
+    return 0;
+}
+
+int32_t sse_reduce_bins(sse_walkers *w, const int32_t *group, int32_t n_groups, double *sums, int64_t *counts, int32_t reset) {
+    if (!w || !sums || !counts) return fail("null argument");
+    if (n_groups < 1) return fail("sse_reduce_bins: n_groups must be positive");
+    const int W = w->dw.W, ncol = w->dw.n_obs + 2;
+    CU(cudaSetDevice(w->model->device));
+    // group -> walkers (CSR), walker order inside a group
+    std::vector<int32_t> start(n_groups + 1, 0), members(W);
+    for (int i = 0; i < W; ++i) {
+        const int g = group ? group[i] : 0;
+        if (g < 0 || g >= n_groups) return fail("sse_reduce_bins: group index out of range at walker " + std::to_string(i));
+        ++start[g + 1];
+    }
+    for (int g = 0; g < n_groups; ++g) start[g + 1] += start[g];
+    {
+        std::vector<int32_t> fill(start.begin(), start.end() - 1);
+        for (int i = 0; i < W; ++i) members[fill[group ? group[i] : 0]++] = i;
+    }
+    const size_t b_out = sizeof(double) * (size_t)n_groups * ncol, b_start = sizeof(int32_t) * (n_groups + 1), b_mem = sizeof(int32_t) * W;
+    const size_t off_start = (b_out + 15) & ~(size_t)15, off_mem = (off_start + b_start + 15) & ~(size_t)15, need = off_mem + b_mem;
+    if (need > w->red_bytes) {
+        CU(cudaStreamSynchronize(w->stream));
+        if (w->d_red) cudaFree(w->d_red);
+        w->d_red = nullptr;
+        CU(cudaMalloc(&w->d_red, need));
+        w->red_bytes = need;
+    }
+    char *base = static_cast<char *>(w->d_red);
+    double *d_out = reinterpret_cast<double *>(base);
+    CU(cudaMemcpyAsync(base + off_start, start.data(), b_start, cudaMemcpyHostToDevice, w->stream));
+    CU(cudaMemcpyAsync(base + off_mem, members.data(), b_mem, cudaMemcpyHostToDevice, w->stream));
+    const int threads = 128, blocks = (n_groups * ncol + threads - 1) / threads;
+    SSE_LAUNCH_KERNEL(k_reduce_bins, blocks, threads, 0, w->stream, w->dw, reinterpret_cast<const int32_t *>(base + off_start),
+                      reinterpret_cast<const int32_t *>(base + off_mem), (int)n_groups, d_out);
+    CU(cudaGetLastError());
+    if (w->comm) NC(nccl().AllReduce(d_out, d_out, (size_t)n_groups * ncol, 8 /* ncclFloat64 */, 0 /* ncclSum */, w->comm, w->stream));
+    std::vector<double> host((size_t)n_groups * ncol);
+    CU(cudaMemcpyAsync(host.data(), d_out, b_out, cudaMemcpyDeviceToHost, w->stream));
+    if (reset) {
+        CU(cudaMemsetAsync(w->dw.acc, 0, sizeof(double) * (size_t)W * w->dw.n_obs, w->stream));
+        CU(cudaMemsetAsync(w->dw.acc_cnt, 0, sizeof(long long) * (size_t)W * 2, w->stream));
+    }
+    CU(cudaStreamSynchronize(w->stream));  // also keeps start/members alive until their copies are done
+    for (int g = 0; g < n_groups; ++g) {
+        for (int i = 0; i < w->dw.n_obs; ++i) sums[(size_t)g * w->dw.n_obs + i] = host[(size_t)g * ncol + i];
+        counts[2 * g] = (int64_t)host[(size_t)g * ncol + w->dw.n_obs];
+        counts[2 * g + 1] = (int64_t)host[(size_t)g * ncol + w->dw.n_obs + 1];
+    }
+    return check_flags(w);
 }
 
 int32_t sse_fetch_counters(sse_walkers *w, uint64_t out[SSE_N_COUNTERS], int32_t reset) {
@@ -750,6 +916,68 @@ int32_t sse_set_temperature(sse_walkers *w, const double *T) {
     for (int i = 0; i < w->dw.W; ++i)
         if (!(T[i] > 0)) return fail("sse_set_temperature: temperatures must be positive");
     return set_field(w, CTL_OFF(T), T);  // src/sse.jl:403
+}
+
+int32_t sse_get_temperatures(sse_walkers *w, double *T) {
+    if (!w || !T) return fail("null argument");
+    std::vector<double> t;
+    if (int32_t s = get_field(w, CTL_OFF(T), t)) return s;
+    std::copy(t.begin(), t.end(), T);
+    return 0;
+}
+
+int32_t sse_pt_set_ladder(sse_walkers *w, const int32_t *walker_at_rank, int32_t n) {
+    if (!w || !walker_at_rank) return fail("null argument");
+    if (n < 2 || n > w->dw.W) return fail("sse_pt_set_ladder: need 2 <= n <= n_walkers");
+    std::vector<char> seen(w->dw.W, 0);
+    for (int i = 0; i < n; ++i) {
+        const int x = walker_at_rank[i];
+        if (x < 0 || x >= w->dw.W || seen[x]) return fail("sse_pt_set_ladder: walker indices must be distinct and in range");
+        seen[x] = 1;
+    }
+    CU(cudaSetDevice(w->model->device));
+    CU(cudaStreamSynchronize(w->stream));
+    if (w->d_ladder) { cudaFree(w->d_ladder); w->d_ladder = nullptr; }
+    CU(cudaMalloc((void **)&w->d_ladder, sizeof(int32_t) * ((size_t)n + 1)));  // [n] = accept counter
+    CU(cudaMemcpyAsync(w->d_ladder, walker_at_rank, sizeof(int32_t) * n, cudaMemcpyHostToDevice, w->stream));
+    CU(cudaStreamSynchronize(w->stream));
+    w->n_ladder = n;
+    return 0;
+}
+
+int32_t sse_pt_get_ladder(sse_walkers *w, int32_t *walker_at_rank) {
+    if (!w || !walker_at_rank) return fail("null argument");
+    if (!w->d_ladder) return fail("sse_pt_get_ladder: no ladder set");
+    CU(cudaMemcpyAsync(walker_at_rank, w->d_ladder, sizeof(int32_t) * w->n_ladder, cudaMemcpyDeviceToHost, w->stream));
+    CU(cudaStreamSynchronize(w->stream));
+    return 0;
+}
+
+int32_t sse_pt_exchange(sse_walkers *w, int32_t parity, uint64_t seed, uint64_t step, int32_t *n_accepted) {
+    if (!w) return fail("null handle");
+    if (!w->d_ladder) return fail("sse_pt_exchange: call sse_pt_set_ladder first");
+    if (parity != 0 && parity != 1) return fail("sse_pt_exchange: parity must be 0 or 1");
+    if (int32_t s = require_between_sweeps(w, "sse_pt_exchange")) return s;
+    CU(cudaSetDevice(w->model->device));
+    int32_t *cnt = w->d_ladder + w->n_ladder;
+    CU(cudaMemsetAsync(cnt, 0, sizeof(int32_t), w->stream));
+    const int pairs = (w->n_ladder - parity) / 2;
+    if (pairs > 0) {
+        SSE_LAUNCH_KERNEL(k_pt_exchange, (pairs + 127) / 128, 128, 0, w->stream, w->dw, w->d_ladder, w->n_ladder, (int)parity,
+                          (unsigned long long)seed, (unsigned long long)step, cnt);
+        CU(cudaGetLastError());
+    }
+    if (n_accepted) {
+        CU(cudaMemcpyAsync(n_accepted, cnt, sizeof(int32_t), cudaMemcpyDeviceToHost, w->stream));
+        CU(cudaStreamSynchronize(w->stream));
+    }
+    return 0;
+}
+
+int32_t sse_pt_uniforms(uint64_t seed, uint64_t step, int32_t n, double *out) {
+    if (!out || n < 0) return fail("sse_pt_uniforms: bad argument");
+    for (int i = 0; i < n; ++i) out[i] = sse_u01(sse_philox_draw(seed, step, (uint64_t)i));
+    return 0;
 }
 
 int32_t sse_set_controller(sse_walkers *w, double target_worm_length_fraction, double num_worms_attenuation_factor) {

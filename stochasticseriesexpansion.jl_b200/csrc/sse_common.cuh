@@ -46,7 +46,7 @@ constexpr int BOND_SHIFT = 2 + VBITS;                  // 14
 constexpr int RNG_WORDS = 66;                          // 33 Philox blocks x 2 draws (see phase_diag_build)
 constexpr int PHASE_WARPS = 4;                         // warps per CTA of sse::k_phase (one warp = one walker)
 constexpr int SWEEP_MAX_WARPS = 16;                    // warps per CTA of sse::k_sweep (launch bounds 512 x 1: 128 registers per thread)
-constexpr int ROT_MARGIN = 64;                         // ring slack kept between the write head and unread old records
+constexpr int ROT_MARGIN = 128;                        // ring slack kept between the write head and unread old records
 
 __host__ __device__ __forceinline__ uint32_t op_pack(uint32_t bond, uint32_t gv, uint32_t diag) {
     return 1u | (diag << 1) | (gv << 2) | (bond << BOND_SHIFT);
@@ -208,12 +208,17 @@ __host__ __device__ __forceinline__ uint4 rec_pack(uint32_t op, uint32_t l0, uin
     r.w = (l2 >> 16) | (l3 << 8);
     return r;
 }
-// overwrite the leg link named by `target` (k << 2 | leg) of the generation at G with `value` (three byte stores)
+// overwrite the leg link named by `target` (k << 2 | leg) of the generation at G with `value`: the 3-byte field starts
+// at byte 4 + 3*leg of the record, so it is one aligned 16-bit store and one byte store
 __device__ __forceinline__ void rec_patch(uint4 *rec, uint32_t G, uint32_t Rcap, uint32_t target, uint32_t value) {
     uint8_t *b = reinterpret_cast<uint8_t *>(rec + ring(G, Rcap, target >> 2)) + 4u + 3u * (target & 3u);
-    b[0] = (uint8_t)value;
-    b[1] = (uint8_t)(value >> 8);
-    b[2] = (uint8_t)(value >> 16);
+    if (target & 1u) {  // odd offset: byte, then aligned half-word
+        b[0] = (uint8_t)value;
+        *reinterpret_cast<uint16_t *>(b + 1) = (uint16_t)(value >> 8);
+    } else {            // even offset: aligned half-word, then byte
+        *reinterpret_cast<uint16_t *>(b) = (uint16_t)value;
+        b[2] = (uint8_t)(value >> 16);
+    }
 }
 
 __device__ __forceinline__ double shfl_f64(double v, int src) {
@@ -262,10 +267,11 @@ __device__ __forceinline__ SmTab stage_tables(const DevModel &dm, uint8_t *smem)
     return st;
 }
 
-// bytes of shared scratch of one streaming warp: random draws + (level 1) state[N], mark[N]
+// bytes of shared scratch of one streaming warp: random draws + (level >= 1) state[N], mark[N] + (level 2) vlast[N]
 __host__ __device__ inline int stream_scratch_bytes(int n_sites, int level) {
     int b = ((RNG_WORDS * 8) + 15) & ~15;
     if (level >= 1) b += 2 * ((n_sites + 15) & ~15);
+    if (level >= 2) b += 4 * ((n_sites + 3) & ~3);
     return b;
 }
 
@@ -286,7 +292,7 @@ __device__ __forceinline__ Ctx ctx_open(const DevModel &dm, const DevWalkers &dw
     c.words = dw.words + (size_t)w * dw.Mw_cap;
     c.rec = dw.rec + (size_t)w * dw.R_cap;
     c.vfirst = dw.vfirst + (size_t)w * N;
-    c.vlast = dw.vlast + (size_t)w * N;
+    c.vlast = level >= 2 ? reinterpret_cast<uint32_t *>(c.mark + ((N + 15) & ~15)) : dw.vlast + (size_t)w * N;
     c.inj = dw.inj ? dw.inj + (size_t)w * dw.inj_len : nullptr;
     c.inj_len = dw.inj_len;
     c.seed = dw.seed;

@@ -82,7 +82,64 @@ struct OpReader {
 // diagonal_update (src/sse.jl:137-191) fused with make_vertex_list! (src/vertex_list.jl:15-54).
 // do_diag = false rebuilds the records of the unchanged string (make_vertex_list! alone).
 // Reads generation g of the record ring (op codes only) and writes generation g+1 (op codes + links) behind it.
+//
+// The pass is a two-stage software pipeline over 32-slot chunks, because a warp that waits for every global load in
+// turn spends its time on L2 round trips (measured: 7400 cycles per chunk).  What a chunk needs from global memory
+// depends only on the OLD string: the random-stream offset of a slot follows from the pre-update slot types before it
+// (2 draws per identity slot, 1 per diagonal operator, Appendix A), so the draws, the proposed bonds and the bond-table
+// rows of chunk c+1 are fetched (stage B) while chunk c is decided and linked (stage C) from registers and shared memory.
 // ------------------------------------------------------------------------------------------------------
+struct ChunkIn {  // what stage B hands to stage C
+    uint32_t op, bond, idm, dgm, kold0;
+    double r;
+    uint4 bi;
+};
+
+template <bool INJ>
+__device__ __forceinline__ ChunkIn diag_stage_b(const DevModel &dm, const Ctx &c, OpReader &rd, int ch, int M, bool do_diag,
+                                                unsigned long long &draws) {
+    const uint32_t lane = c.lane, lt = rd.lt;
+    ChunkIn in;
+    uint32_t obits;
+    in.kold0 = rd.next(ch, obits, in.op);
+    const int p = ch * 32 + (int)lane;
+    const bool nonid = in.op != 0u;
+    const bool is_id = (p < M) && !nonid;
+    const bool is_dg = nonid && (in.op & 2u);
+    in.bond = op_bond(in.op);
+    in.r = 0.0;
+    in.idm = 0;
+    in.dgm = 0;
+    if (do_diag) {
+        // stream offsets: 2 draws per identity slot, 1 per diagonal operator, in slot order (Appendix A)
+        in.idm = __ballot_sync(FULL, is_id);
+        in.dgm = __ballot_sync(FULL, is_dg);
+        const uint32_t D = 2u * __popc(in.idm) + __popc(in.dgm);
+        if (D) {
+            const unsigned long long my = draws + 2u * __popc(in.idm & lt) + __popc(in.dgm & lt);
+            const unsigned long long j0 = draws >> 1;
+            fill_draws<INJ>(c, j0);
+            if (!INJ && (draws & 1ull) && D == 64u && lane == 0) {  // the one draw beyond 32 blocks
+                uint32_t b[4];
+                sse_philox_block(c.seed, c.wid, j0 + 32, b);
+                reinterpret_cast<uint4 *>(c.rng)[32] = make_uint4(b[0], b[1], b[2], b[3]);
+            }
+            __syncwarp();
+            if (is_id) {
+                in.bond = (uint32_t)sse_uint_below(scratch_draw<INJ>(c, j0, my), (uint64_t)dm.n_bonds);  // rand(rng, 1:N_b) - 1 (sse.jl:152)
+                in.r = sse_u01(scratch_draw<INJ>(c, j0, my + 1));                                         // sse.jl:166
+            } else if (is_dg) {
+                in.r = sse_u01(scratch_draw<INJ>(c, j0, my));                                             // sse.jl:178
+            }
+            draws += D;
+            __syncwarp();  // the scratch is refilled for the next chunk
+        }
+    }
+    in.bi = make_uint4(0, 0, 0, 0);
+    if (is_id || nonid) in.bi = __ldg(dm.bond_info + in.bond);
+    return in;
+}
+
 template <bool INJ>
 __device__ void phase_diag_build(const SmTab &st, const DevModel &dm, const DevWalkers &dw, Ctx &c, bool do_diag) {
     const uint32_t lane = c.lane, lt = lanemask_lt();
@@ -95,7 +152,6 @@ __device__ void phase_diag_build(const SmTab &st, const DevModel &dm, const DevW
     for (int s = lane; s < N; s += 32) { c.vfirst[s] = NONE32; c.vlast[s] = NONE32; }
     __syncwarp();
     const int M = c.M;
-    const uint32_t Nb = (uint32_t)dm.n_bonds;
     const double p_make_bond_raw = (double)dm.n_bonds / c.T;   // sse.jl:147
     const double p_remove_bond_raw = c.T / (double)dm.n_bonds; // sse.jl:148
     const uint32_t Rcap = c.Rcap, n_old = (uint32_t)c.n;
@@ -107,49 +163,27 @@ __device__ void phase_diag_build(const SmTab &st, const DevModel &dm, const DevW
     OpReader rd;
     rd.init(c.words, c.rec, c.G, Rcap, nchunks, lane);
     uint2 wout = make_uint2(0u, 0u);  // new {bits, rank} of chunk 32*j + lane, written 32 words at a time
+    // accept thresholds (see below), valid while the operator count stays inside [win_lo, win_hi]
+    int win_lo = 1, win_hi = 0;
+    double pm_lo = 0, pm_hi = 0, rm_sure = 0, rm_maybe = 0;
 
+    ChunkIn in = diag_stage_b<INJ>(dm, c, rd, 0, M, do_diag, draws);
     for (int ch = 0; ch < nchunks; ++ch) {
+        ChunkIn nxt = in;
+        if (ch + 1 < nchunks) nxt = diag_stage_b<INJ>(dm, c, rd, ch + 1, M, do_diag, draws);  // stage B of the next chunk
+        // ------------------------------ stage C of chunk ch ------------------------------
         const int p = ch * 32 + (int)lane;
         const bool active = p < M;
-        uint32_t obits, op;
-        const uint32_t kold0 = rd.next(ch, obits, op);
+        const uint32_t op = in.op;
         const bool nonid = op != 0u;
         const bool is_id = active && !nonid;
         const bool is_dg = nonid && (op & 2u);
         const bool is_off = nonid && !(op & 2u);
-        uint32_t bond = op_bond(op);
-        const uint32_t gv = op_gv(op);
-        uint32_t newop = op;
-        double r = 0.0;
-        uint32_t idm = 0, dgm = 0;
-
-        if (do_diag) {
-            // stream offsets: 2 draws per identity slot, 1 per diagonal operator, in slot order (Appendix A)
-            idm = __ballot_sync(FULL, is_id);
-            dgm = __ballot_sync(FULL, is_dg);
-            const uint32_t D = 2u * __popc(idm) + __popc(dgm);
-            if (D) {
-                const unsigned long long my = draws + 2u * __popc(idm & lt) + __popc(dgm & lt);
-                const unsigned long long j0 = draws >> 1;
-                fill_draws<INJ>(c, j0);
-                if (!INJ && (draws & 1ull) && D == 64u && lane == 0) {  // the one draw beyond 32 blocks
-                    uint32_t b[4];
-                    sse_philox_block(c.seed, c.wid, j0 + 32, b);
-                    reinterpret_cast<uint4 *>(c.rng)[32] = make_uint4(b[0], b[1], b[2], b[3]);
-                }
-                __syncwarp();
-                if (is_id) {
-                    bond = (uint32_t)sse_uint_below(scratch_draw<INJ>(c, j0, my), Nb);  // rand(rng, 1:N_b) - 1 (sse.jl:152)
-                    r = sse_u01(scratch_draw<INJ>(c, j0, my + 1));                      // sse.jl:166
-                } else if (is_dg) {
-                    r = sse_u01(scratch_draw<INJ>(c, j0, my));                          // sse.jl:178
-                }
-                draws += D;
-            }
-        }
-        uint4 bi = make_uint4(0, 0, 0, 0);
-        if (is_id || nonid) bi = __ldg(dm.bond_info + bond);
+        const uint32_t bond = in.bond, gv = op_gv(op), idm = in.idm, dgm = in.dgm;
+        const double r = in.r;
+        const uint4 bi = in.bi;
         const uint32_t sa = bi.x & NONE24, sb = bi.y & NONE24;
+        uint32_t newop = op;
 
         if (do_diag) {
             // State seen by each identity slot = state at chunk start overridden by earlier off-diagonal
@@ -219,20 +253,27 @@ __device__ void phase_diag_build(const SmTab &st, const DevModel &dm, const DevW
             }
             // Accept tests (sse.jl:164-166,176-178) depend on the running operator count n.  Within the chunk
             // n stays in [n - #diagonal, n + #identity]; both tests are monotone in n (IEEE division and
-            // multiplication are monotone), so evaluating them at the two ends decides every lane whose draw is
-            // not between the two thresholds.  Only if some lane is undecided (probability ~ 64/(M-n) per chunk)
-            // the in-order recurrence is solved exactly by fixed-point iteration.
+            // multiplication are monotone), so evaluating them at the two ends of a window that contains this
+            // range decides every lane whose draw is not between the two thresholds.  The window (and its two
+            // divisions) is kept for as many chunks as n stays inside it.  Only if some lane is undecided
+            // (probability ~ 600/(M-n) per chunk) the in-order recurrence is solved exactly by fixed-point iteration.
             const int n_lo = n - __popc(dgm), n_hi = n + __popc(idm);
+            if (n_lo < win_lo || n_hi > win_hi) {
+                win_lo = n_lo - 256;
+                win_hi = n_hi + 256;
+                pm_lo = p_make_bond_raw / (double)(M - win_lo);
+                pm_hi = (M - win_hi > 0) ? p_make_bond_raw / (double)(M - win_hi) : __longlong_as_double(0x7ff0000000000000ll);
+                rm_sure = (double)(M - win_hi + 1) * p_remove_bond_raw;
+                rm_maybe = (double)(M - win_lo + 1) * p_remove_bond_raw;
+            }
             bool acc = false, amb = false;
             if (is_id) {
-                const double pm_lo = p_make_bond_raw / (double)(M - n_lo);
-                const double pm_hi = (M - n_hi > 0) ? p_make_bond_raw / (double)(M - n_hi) : __longlong_as_double(0x7ff0000000000000ll);
                 acc = r < pm_lo * w;
                 amb = !acc && (r < pm_hi * w);
             } else if (is_dg) {
                 const double rw = r * w;
-                acc = rw < (double)(M - n_hi + 1) * p_remove_bond_raw;
-                amb = !acc && (rw < (double)(M - n_lo + 1) * p_remove_bond_raw);
+                acc = rw < rm_sure;
+                amb = !acc && (rw < rm_maybe);
             }
             uint32_t ins, rem;
             if (__ballot_sync(FULL, amb)) {
@@ -268,10 +309,10 @@ __device__ void phase_diag_build(const SmTab &st, const DevModel &dm, const DevW
         const uint32_t nm = __ballot_sync(FULL, nn);
         const uint32_t cnt = __popc(nm);
         const uint32_t k = kbase + __popc(nm & lt);
-        // capacity: n_cap records, and the write head must stay clear of old records that are not consumed yet (this
-        // chunk's are in registers, the next chunk's are requested: ROT_MARGIN covers both)
+        // capacity: n_cap records, and the write head must stay clear of old records that are not consumed yet (the
+        // reader is two chunks ahead of this point: ROT_MARGIN covers them)
         if ((long long)kbase + cnt > dw.n_cap ||
-            (long long)n_old + kbase + cnt + ROT_MARGIN > (long long)Rcap + kold0) {
+            (long long)n_old + kbase + cnt + ROT_MARGIN > (long long)Rcap + in.kold0) {
             c.flags |= SSE_FLAG_N_OVERFLOW;
             return;
         }
@@ -334,6 +375,7 @@ __device__ void phase_diag_build(const SmTab &st, const DevModel &dm, const DevW
             if (wi <= ch) c.words[wi] = wout;
         }
         kbase += cnt;
+        in = nxt;
         __syncwarp();
     }
     // periodic closure (vertex_list.jl:46-51)
@@ -403,88 +445,103 @@ __device__ void worm_finish(const SmTab &st, const DevModel &dm, const DevWalker
 // with the table-driven MagnetizationEstimator init/measure/result (magnetization_estimator.jl:96-230).
 // out[n_obs] (global) receives the observables.
 // ------------------------------------------------------------------------------------------------------
+// One pass over the string serves the sign and up to MEASURE_GROUP estimators at once (every pass re-reads all op codes).
+constexpr int MEASURE_GROUP = 2;
+
 __device__ void phase_measure(const SmTab &st, const DevModel &dm, const DevWalkers &dw, Ctx &c, double *out) {
     const uint32_t lane = c.lane;
     const int M = c.M;
     const int nchunks = (M + 31) >> 5;
-    uint32_t neg = 0;
-    {
-        OpReader rd;
-        rd.init(c.words, c.rec, c.G, c.Rcap, nchunks, lane);
-        for (int ch = 0; ch < nchunks; ++ch) {
-            uint32_t bits, op;
-            rd.next(ch, bits, op);
-            neg += __popc(__ballot_sync(FULL, op != 0u && st.vneg[op_gv(op)]));
-        }
-    }
-    const double sign = (neg & 1u) ? -1.0 : 1.0;  // sse.jl:313
-    const double nops = (double)c.n;
-    if (lane == 0) {
-        out[SSE_OBS_SIGN] = sign;
-        out[SSE_OBS_OPERATOR_COUNT] = nops;
-        out[SSE_OBS_SIGN_OPERATOR_COUNT] = sign * nops;
-        out[SSE_OBS_SIGN_OPERATOR_COUNT2] = sign * (nops * nops);
-        out[SSE_OBS_SIGN_ENERGY] = -sign * (nops * c.T + dm.energy_offset) / (double)dm.norm_sites;
-        out[SSE_OBS_WORM_LENGTH_FRACTION] = c.last_wlf;
-    }
     const int N = dm.n_sites, md = dm.est_max_dim;
-    for (int e = 0; e < dm.n_est; ++e) {
-        const double *ev = dm.est_values + (size_t)e * N * md;
-        // init (magnetization_estimator.jl:96-123)
-        double part = 0.0;
-        for (int s = lane; s < N; s += 32) part += __ldg(ev + (size_t)s * md + (c.state[s] - 1));
-        double tmpmag = warp_sum_f64(part);
-        double mag = 0, absmag = 0, mag2 = 0, mag4 = 0;  // per-lane partial sums
-        if (lane == 0) { mag = tmpmag; absmag = fabs(tmpmag); mag2 = tmpmag * tmpmag; mag4 = mag2 * mag2; }
+    const double nops = (double)c.n;
+    double sign = 1.0;
+    for (int e0 = 0; e0 == 0 || e0 < dm.n_est; e0 += MEASURE_GROUP) {
+        const int ne = (dm.n_est - e0 < MEASURE_GROUP) ? dm.n_est - e0 : MEASURE_GROUP;  // may be 0: the sign alone
+        const double *ev[MEASURE_GROUP];
+        double tmpmag[MEASURE_GROUP], mag[MEASURE_GROUP], absmag[MEASURE_GROUP], mag2[MEASURE_GROUP], mag4[MEASURE_GROUP];
+#pragma unroll
+        for (int g = 0; g < MEASURE_GROUP; ++g) {
+            ev[g] = dm.est_values + (size_t)(e0 + (g < ne ? g : 0)) * N * md;
+            // init (magnetization_estimator.jl:96-123)
+            double part = 0.0;
+            if (g < ne)
+                for (int s = lane; s < N; s += 32) part += __ldg(ev[g] + (size_t)s * md + (c.state[s] - 1));
+            tmpmag[g] = warp_sum_f64(part);
+            mag[g] = absmag[g] = mag2[g] = mag4[g] = 0.0;  // per-lane partial sums
+            if (lane == 0) { mag[g] = tmpmag[g]; absmag[g] = fabs(tmpmag[g]); mag2[g] = tmpmag[g] * tmpmag[g]; mag4[g] = mag2[g] * mag2[g]; }
+        }
+        uint32_t neg = 0;
         OpReader rd;
         rd.init(c.words, c.rec, c.G, c.Rcap, nchunks, lane);
         for (int ch = 0; ch < nchunks; ++ch) {
             uint32_t bits, op;
             rd.next(ch, bits, op);
             const bool nonid = op != 0u;
-            double delta = 0.0;
-            if (nonid && !(op & 2u)) {  // off-diagonal: tmpmag += sum_l sign*(m(top_l) - m(bottom_l)) (:134-150)
-                const uint4 bi = __ldg(dm.bond_info + op_bond(op));
-                const uint32_t vi = st.vinfo[op_gv(op)];
-                const double *ea = ev + (size_t)(bi.x & NONE24) * md, *eb = ev + (size_t)(bi.y & NONE24) * md;
-                delta = (__ldg(ea + ((vi >> 16) & 0xffu) - 1) - __ldg(ea + (vi & 0xffu) - 1)) +
-                        (__ldg(eb + (vi >> 24) - 1) - __ldg(eb + ((vi >> 8) & 0xffu) - 1));
+            if (e0 == 0) neg += __popc(__ballot_sync(FULL, nonid && st.vneg[op_gv(op)]));  // measure_sign (sse.jl:305-314)
+            if (ne == 0) continue;
+            const bool off = nonid && !(op & 2u);
+            const uint32_t offm = __ballot_sync(FULL, off);
+            uint4 bi = make_uint4(0, 0, 0, 0);
+            uint32_t vi = 0;
+            if (off) {
+                bi = __ldg(dm.bond_info + op_bond(op));
+                vi = st.vinfo[op_gv(op)];
             }
-            const uint32_t offm = __ballot_sync(FULL, delta != 0.0);
-            double scan = delta;  // inclusive prefix sum over the chunk, in slot order
-            if (offm) {
 #pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const double up = shfl_up_f64(scan, d);
-                    if ((int)lane >= d) scan += up;
+            for (int g = 0; g < MEASURE_GROUP; ++g) {
+                if (g >= ne) break;
+                double scan = 0.0;
+                if (off) {  // off-diagonal: tmpmag += sum_l sign*(m(top_l) - m(bottom_l)) (:134-150)
+                    const double *ea = ev[g] + (size_t)(bi.x & NONE24) * md, *eb = ev[g] + (size_t)(bi.y & NONE24) * md;
+                    scan = (__ldg(ea + ((vi >> 16) & 0xffu) - 1) - __ldg(ea + (vi & 0xffu) - 1)) +
+                           (__ldg(eb + (vi >> 24) - 1) - __ldg(eb + ((vi >> 8) & 0xffu) - 1));
                 }
+                if (offm) {  // inclusive prefix sum over the chunk, in slot order
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const double up = shfl_up_f64(scan, d);
+                        if ((int)lane >= d) scan += up;
+                    }
+                }
+                if (nonid) {  // every non-identity operator is one sample (:152-158)
+                    const double v = tmpmag[g] + scan, v2 = v * v;
+                    mag[g] += v;
+                    absmag[g] += fabs(v);
+                    mag2[g] += v2;
+                    mag4[g] += v2 * v2;
+                }
+                if (offm) tmpmag[g] += shfl_f64(scan, 31);
             }
-            if (nonid) {  // every non-identity operator is one sample (:152-158)
-                const double v = tmpmag + scan, v2 = v * v;
-                mag += v;
-                absmag += fabs(v);
-                mag2 += v2;
-                mag4 += v2 * v2;
-            }
-            if (offm) tmpmag += shfl_f64(scan, 31);
         }
-        mag = warp_sum_f64(mag);
-        absmag = warp_sum_f64(absmag);
-        mag2 = warp_sum_f64(mag2);
-        mag4 = warp_sum_f64(mag4);
-        if (lane == 0) {  // result (:205-230)
-            const double ns = 1.0 + nops;
-            const double norm = 1.0 / (double)dm.norm_sites;
-            mag *= norm;
-            absmag *= norm;
-            mag2 *= norm * norm;
-            mag4 *= (norm * norm) * (norm * norm);
-            double *o = out + SSE_OBS_FIXED + SSE_OBS_PER_ESTIMATOR * e;
-            o[0] = sign * mag / ns;
-            o[1] = sign * absmag / ns;
-            o[2] = sign * mag2 / ns;
-            o[3] = sign * mag4 / ns;
-            o[4] = sign * (1.0 / c.T / (ns + 1.0) / ns * (mag * mag + mag2) * (double)dm.norm_sites);
+        if (e0 == 0) {
+            sign = (neg & 1u) ? -1.0 : 1.0;  // sse.jl:313
+            if (lane == 0) {
+                out[SSE_OBS_SIGN] = sign;
+                out[SSE_OBS_OPERATOR_COUNT] = nops;
+                out[SSE_OBS_SIGN_OPERATOR_COUNT] = sign * nops;
+                out[SSE_OBS_SIGN_OPERATOR_COUNT2] = sign * (nops * nops);
+                out[SSE_OBS_SIGN_ENERGY] = -sign * (nops * c.T + dm.energy_offset) / (double)dm.norm_sites;
+                out[SSE_OBS_WORM_LENGTH_FRACTION] = c.last_wlf;
+            }
+        }
+#pragma unroll
+        for (int g = 0; g < MEASURE_GROUP; ++g) {
+            if (g >= ne) break;
+            double m1 = warp_sum_f64(mag[g]), ma = warp_sum_f64(absmag[g]), m2 = warp_sum_f64(mag2[g]), m4 = warp_sum_f64(mag4[g]);
+            if (lane == 0) {  // result (:205-230)
+                const double ns = 1.0 + nops;
+                const double norm = 1.0 / (double)dm.norm_sites;
+                m1 *= norm;
+                ma *= norm;
+                m2 *= norm * norm;
+                m4 *= (norm * norm) * (norm * norm);
+                double *o = out + SSE_OBS_FIXED + SSE_OBS_PER_ESTIMATOR * (e0 + g);
+                o[0] = sign * m1 / ns;
+                o[1] = sign * ma / ns;
+                o[2] = sign * m2 / ns;
+                o[3] = sign * m4 / ns;
+                o[4] = sign * (1.0 / c.T / (ns + 1.0) / ns * (m1 * m1 + m2) * (double)dm.norm_sites);
+            }
         }
     }
     __syncwarp();

@@ -1,4 +1,5 @@
-"""Replica exchange (parallel tempering) over the walkers of a batch — host-side decisions only.
+"""Replica exchange (parallel tempering) over the walkers of a batch: decided on the host (ReplicaExchange) or on the
+device (DeviceReplicaExchange, sse_pt_exchange).
 
 The reference exposes two hooks to Carlo's parallel-tempering wrapper (src/sse.jl:390-405):
 `parallel_tempering_log_weight_ratio(mc, :T, T_new) = -n * log(T_new / T)` and
@@ -43,7 +44,11 @@ class ReplicaExchange:
         self.proposed = 0
         self.accepted = 0
 
-    def step(self):
+    def step(self, allow_open_bin: bool = False):
+        if not allow_open_bin:  # the accumulators are indexed by walker: a bin must not span a change of temperature
+            _, counts = self.walkers.fetch_accumulators(reset=False)
+            if counts.any():
+                raise RuntimeError("a bin is open: flush the accumulators before exchanging temperatures")
         n = self.walkers.num_operators()
         T = np.array(self.walkers.T, dtype=np.float64)
         order = np.argsort(T, kind="stable")
@@ -55,3 +60,52 @@ class ReplicaExchange:
         self.parity ^= 1
         self.walkers.set_temperature(T_new)
         return T_new
+
+
+def pt_uniforms(seed: int, step: int, n: int) -> np.ndarray:
+    """The uniforms sse_pt_exchange(seed, step) uses for its pairs 0..n-1 (draw i of the Philox stream (seed, step))."""
+    import ctypes as C
+
+    from . import capi
+
+    out = np.zeros(max(n, 1))
+    capi.check(capi.lib().sse_pt_uniforms(int(seed), int(step), int(n), out.ctypes.data_as(capi.f64p)))
+    return out[:n]
+
+
+class DeviceReplicaExchange:
+    """Neighbour swaps decided on the device (sse_pt_set_ladder / sse_pt_exchange): per exchange step one small kernel and a
+    4-byte read-back instead of a round trip of operator counts and temperatures.  Measurements belong to a TEMPERATURE,
+    not to a walker: `rank_of_walker()` gives the group index to pass to Walkers.reduce_bins, and bins must be flushed
+    before every exchange step (step() refuses to run on a non-empty bin unless told otherwise)."""
+
+    def __init__(self, walkers, seed: int = 0):
+        self.walkers = walkers
+        self.seed = int(seed)
+        self.step_index = 0
+        self.parity = 0
+        self.proposed = 0
+        self.accepted = 0
+        order = np.argsort(np.asarray(walkers.T, dtype=np.float64), kind="stable")
+        walkers.pt_set_ladder(order)
+
+    def rank_of_walker(self) -> np.ndarray:
+        ladder = self.walkers.pt_get_ladder()
+        rank = np.empty(len(ladder), dtype=np.int32)
+        rank[ladder] = np.arange(len(ladder), dtype=np.int32)
+        return rank
+
+    def step(self, allow_open_bin: bool = False) -> int:
+        if not allow_open_bin:
+            _, counts = self.walkers.fetch_accumulators(reset=False)
+            if counts.any():
+                raise RuntimeError("a bin is open: flush the accumulators (reduce_bins / fetch_accumulators) before exchanging "
+                                   "temperatures, or a bin mixes measurements taken at different temperatures")
+        n = self.walkers._n_ladder
+        pairs = max(0, (n - self.parity) // 2)
+        acc = self.walkers.pt_exchange(self.parity, self.seed, self.step_index)
+        self.proposed += pairs
+        self.accepted += acc
+        self.parity ^= 1
+        self.step_index += 1
+        return acc

@@ -143,6 +143,28 @@ class Walkers:
         check(self.L.sse_fetch_accumulators(self.handle, sums.ctypes.data_as(f64p), counts.ctypes.data_as(i64p), int(reset)))
         return sums, counts
 
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        """ncclUniqueId for comm_init (rank 0 creates it, the host broadcasts it)."""
+        buf = C.create_string_buffer(128)
+        check(capi.lib().sse_comm_unique_id(buf))
+        return buf.raw
+
+    def comm_init(self, unique_id: bytes, rank: int, nranks: int):
+        """Join the NCCL communicator used by reduce_bins (one rank per GPU)."""
+        assert len(unique_id) == 128
+        check(self.L.sse_comm_init(self.handle, C.create_string_buffer(unique_id, 128), int(rank), int(nranks)))
+
+    def reduce_bins(self, group=None, n_groups: int = 1, reset: bool = True):
+        """One bin: per-group sums of the accumulators over this rank's walkers and, after comm_init, over all ranks
+        (sse_reduce_bins).  Returns (sums[n_groups, n_obs], counts[n_groups, 2])."""
+        g = None if group is None else np.ascontiguousarray(group, dtype=np.int32)
+        sums = np.zeros((n_groups, self.n_obs))
+        counts = np.zeros((n_groups, 2), dtype=np.int64)
+        check(self.L.sse_reduce_bins(self.handle, None if g is None else g.ctypes.data_as(capi.i32p), int(n_groups),
+                                     sums.ctypes.data_as(f64p), counts.ctypes.data_as(i64p), int(reset)))
+        return sums, counts
+
     def accumulators_device_ptr(self):
         s, c = C.c_void_p(), C.c_void_p()
         check(self.L.sse_accumulators_device_ptr(self.handle, C.byref(s), C.byref(c)))
@@ -202,6 +224,29 @@ class Walkers:
         assert len(t) == self.n_walkers
         check(self.L.sse_set_temperature(self.handle, t.ctypes.data_as(f64p)))
         self.T = t
+
+    def temperatures(self) -> np.ndarray:
+        t = np.zeros(self.n_walkers)
+        check(self.L.sse_get_temperatures(self.handle, t.ctypes.data_as(f64p)))
+        return t
+
+    def pt_set_ladder(self, walker_at_rank):
+        """Name the walkers of a temperature ladder in rank order (device-side replica exchange, sse_pt_exchange)."""
+        o = np.ascontiguousarray(walker_at_rank, dtype=np.int32)
+        check(self.L.sse_pt_set_ladder(self.handle, o.ctypes.data_as(capi.i32p), len(o)))
+        self._n_ladder = len(o)
+
+    def pt_get_ladder(self) -> np.ndarray:
+        o = np.zeros(self._n_ladder, dtype=np.int32)
+        check(self.L.sse_pt_get_ladder(self.handle, o.ctypes.data_as(capi.i32p)))
+        return o
+
+    def pt_exchange(self, parity: int, seed: int, step: int) -> int:
+        """One round of neighbour swaps decided on the device; returns the number of accepted pairs.  self.T is refreshed."""
+        acc = C.c_int32(0)
+        check(self.L.sse_pt_exchange(self.handle, int(parity), int(seed), int(step), C.byref(acc)))
+        self.T = self.temperatures()
+        return int(acc.value)
 
     def set_launch_shape(self, worm_warps: int = 0, stream_warps: int = 0):
         """Launch shape of sweep()/advance(): warps per CTA that chase worms (one lane = one walker) and warps that run the

@@ -203,3 +203,91 @@ def test_gpu_shapes_edge_cases(shape_env):
 @pytest.mark.parametrize("level", [0, 1])
 def test_gpu_shapes_large_lattice_memory_paths(shape_env, level, monkeypatch):
     G.test_large_lattice_memory_paths(level, monkeypatch)
+
+
+def _body_reduce_bins(with_comm):
+    """sse_reduce_bins: per-group sums of the accumulators in walker order (and, with a communicator, the NCCL all-reduce
+    over its ranks: one rank here) equal the host-side sums of sse_fetch_accumulators, and reset the bin."""
+    model = MODEL_CLASSES["heisenberg_eof"]()
+    dm, om = G._pair(model)
+    W = 13
+    Ts = np.repeat([0.4, 0.8, 1.6, 3.2], 4)[:W]
+    group = np.repeat([0, 1, 2, 3], 4)[:W].astype(np.int32)
+    gw = Walkers(dm, Ts, m_capacity=4096, seed=41)
+    if with_comm:
+        gw.comm_init(Walkers.comm_unique_id(), 0, 1)
+    gw.init()
+    gw.sweep(10, thermalized=False)
+    gw.sweep(6, thermalized=True, measure=True)
+    sums, counts = gw.fetch_accumulators(reset=False)
+    gs, gc = gw.reduce_bins(group, 4, reset=True)
+    for g in range(4):
+        sel = group == g
+        expect = np.zeros(gw.n_obs)
+        for i in np.nonzero(sel)[0]:  # the library adds in walker order
+            expect = expect + sums[i]
+        assert np.array_equal(gs[g], expect)
+        assert np.array_equal(gc[g], counts[sel].sum(axis=0))
+    s2, c2 = gw.fetch_accumulators()
+    assert not s2.any() and not c2.any()
+    one, onec = gw.reduce_bins()  # a single group, empty bin
+    assert one.shape == (1, gw.n_obs) and not one.any() and not onec.any()
+    with pytest.raises(SSEError):
+        gw.reduce_bins(group, 3)
+
+
+def test_emu_reduce_bins(emu):
+    _body_reduce_bins(False)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("with_comm", [False, True])
+def test_gpu_reduce_bins(with_comm):
+    _body_reduce_bins(with_comm)
+
+
+def _body_device_replica_exchange():
+    """sse_pt_exchange: the device's swap decisions (log weight ratio of src/sse.jl:395 on the device, uniforms from the
+    Philox stream (seed, step)) equal tempering.swap_decisions fed with the same uniforms; temperatures stay a
+    permutation of the ladder; bins are attributed to temperatures through the ladder."""
+    from helpers import heisenberg_square, isconsistent
+    from sse_b200.tempering import DeviceReplicaExchange, pt_uniforms, swap_decisions
+
+    model = heisenberg_square(4, False)
+    dm, om = G._pair(model)
+    ladder = np.linspace(0.3, 1.2, 11)
+    perm = np.random.default_rng(3).permutation(len(ladder))
+    gw = Walkers(dm, ladder[perm], m_capacity=4096, seed=8)
+    gw.init()
+    gw.sweep(40, thermalized=False)
+    rx = DeviceReplicaExchange(gw, seed=77)
+    assert np.array_equal(gw.pt_get_ladder(), np.argsort(ladder[perm], kind="stable"))
+    for it in range(12):
+        gw.sweep(3, thermalized=True, measure=True)
+        with pytest.raises(RuntimeError):
+            rx.step()                      # a bin is open
+        rank = rx.rank_of_walker()
+        sums, counts = gw.reduce_bins(rank, len(ladder))  # bins by temperature rank
+        assert np.all(counts[:, 0] == 3)
+        n, T = gw.num_operators(), gw.temperatures()
+        order, parity = gw.pt_get_ladder(), rx.parity
+        expect = swap_decisions(n, T, order, parity, pt_uniforms(77, it, len(ladder)))
+        acc = rx.step()
+        T_new = gw.temperatures()
+        assert np.array_equal(T_new, expect) and np.array_equal(gw.T, T_new)
+        assert acc == np.count_nonzero(T_new != T) // 2
+        assert np.array_equal(np.sort(T_new), ladder)
+        assert np.array_equal(T_new[gw.pt_get_ladder()], ladder)  # the ladder stays sorted by temperature
+    assert 0 < rx.accepted <= rx.proposed
+    for i in (0, 5, 10):
+        st = gw.get_state(i)
+        assert st["T"] == gw.T[i] and isconsistent(st["operators"], st["state"], om.sse_data)
+
+
+def test_emu_device_replica_exchange(emu):
+    _body_device_replica_exchange()
+
+
+@pytest.mark.gpu
+def test_gpu_device_replica_exchange():
+    _body_device_replica_exchange()
