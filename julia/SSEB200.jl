@@ -11,6 +11,7 @@ module SSEB200
 
 using Carlo
 using HDF5
+using LinearAlgebra
 import StochasticSeriesExpansion as S
 
 const libsse = get(ENV, "SSE_B200_LIB", "libsse_b200.so")
@@ -136,6 +137,36 @@ mutable struct MC{Model<:S.AbstractModel} <: AbstractMC
     hwalkers::Ptr{Cvoid}
     obs_names::Vector{Symbol}
     nobs::Int
+    sweeps_per_call::Int   # > 1: batched mode, see Carlo.sweep! below
+end
+
+"""
+Upper bound on <n> at temperature `T_min`: <n> = beta * sum_b <W_b> <= beta * sum_b lambda_max(W_b), W_b the (signed)
+vertex-weight matrix of bond b in the compound basis.  Same bound as the Python host (mc.py operator_count_bound).
+"""
+function operator_count_bound(sse_data::S.SSEData{2}, T_min::Real)
+    lam = map(sse_data.vertex_data) do vd
+        d0, d1 = vd.dims
+        W = zeros(d0 * d1, d0 * d1)
+        for v in eachindex(vd.weights)
+            ls = Int.(vd.leg_states[:, v]) .- 1
+            W[ls[1] + d0 * ls[2] + 1, ls[3] + d0 * ls[4] + 1] = vd.weights[v] * vd.signs[v]
+        end
+        eigmax(Symmetric(0.5 .* (W .+ W')))
+    end
+    return sum(lam[b.type] for b in sse_data.bonds) / T_min
+end
+
+"""
+(m_capacity, n_capacity) the string growth rule M <- 1.5 M + 100 while n >= M/2 (src/sse.jl:138-145) cannot exceed:
+M <= 3 n + 100 in the worst case, n <= the spectral bound + 8 sigma.  The device cannot resize a string inside a launch
+(the reference just calls resize!), so the capacity is fixed at creation; both can be overridden with
+params[:m_capacity] / params[:n_capacity], and string slots are cheap (0.25 B each).
+"""
+function default_capacity(sse_data::S.SSEData{2}, T_min::Real)
+    nb = operator_count_bound(sse_data, T_min)
+    nb = nb + 8 * sqrt(nb) + 64
+    return (ceil(Int, 3 * nb) + 1124, min(ceil(Int, nb) + 256, (1 << 22) - 1))
 end
 
 "`MC(params)` — replaces StochasticSeriesExpansion.MC(params) (src/sse.jl:26-45); binds sse_model_create + sse_walkers_create."
@@ -157,8 +188,8 @@ function MC(params::AbstractDict)
             S.normalization_site_count(model), length(ests), f.max_dim, pointer(f.est))
         check(ccall((:sse_model_create, libsse), Int32, (Ref{ModelDesc}, Ref{Ptr{Cvoid}}), desc, hmodel))
     end
-    mcap = get(params, :m_capacity, max(4096, round(Int, 6 * length(sse_data.bonds) / minimum(T)) + 4 * length(sse_data.sites)))
-    opts = WalkersOpts(length(T), pointer(T), mcap, get(params, :n_capacity, min(mcap, 1 << 22)), get(params, :device, -1),
+    mdef, ndef = default_capacity(sse_data, minimum(T))
+    opts = WalkersOpts(length(T), pointer(T), get(params, :m_capacity, mdef), get(params, :n_capacity, ndef), get(params, :device, -1),
         get(params, :seed, 0), get(params, :walker_id_offset, 0), get(params, :target_worm_length_fraction, 2.0),
         get(params, :num_worms_attenuation_factor, 0.01), get(params, :init_num_worms, 5))
     hw = Ref{Ptr{Cvoid}}(C_NULL)
@@ -167,7 +198,7 @@ function MC(params::AbstractDict)
     for E in ests, o in (:mag, :absmag, :mag2, :mag4, :magchi)
         push!(names, S.magnetization_estimator_obs_symbols(S.get_prefix(E))[2][o])
     end
-    mc = MC{typeof(model)}(model, sse_data, ests, T, hmodel[], hw[], names, length(names))
+    mc = MC{typeof(model)}(model, sse_data, ests, T, hmodel[], hw[], names, length(names), get(params, :sweeps_per_call, 1))
     finalizer(mc) do m
         ccall((:sse_walkers_destroy, libsse), Int32, (Ptr{Cvoid},), m.hwalkers)
         ccall((:sse_model_destroy, libsse), Int32, (Ptr{Cvoid},), m.hmodel)
@@ -181,19 +212,42 @@ function Carlo.init!(mc::MC, ctx::MCContext, params::AbstractDict)
         get(params, :init_opstring_cutoff, -1), get(params, :diagonal_warmup_sweeps, 5)))
 end
 
-"Carlo.sweep! (src/sse.jl:62-68) -> sse_sweep + sse_sync"
+"""
+Carlo.sweep! (src/sse.jl:62-68) -> sse_sweep + sse_sync.
+
+Default (`sweeps_per_call = 1`): one launch of one sweep per Carlo step, exactly the reference's call pattern; every step
+then waits for the walker with the most worm work (max ~ 4x the mean, SURVEY H1b) and pays a launch ramp, which costs
+about a third of the device's throughput at BASELINE sizes (bench.py, key `carlo_call_pattern`).
+
+Batched mode (`params[:sweeps_per_call] = k > 1`): one Carlo step = k sweeps inside one persistent launch, measured on the
+device after every sweep once thermalised; `measure!` then pushes the MEAN of those k measurements per walker (a bin of
+k samples — Carlo's binning analysis is unchanged because it only ever sees bin means).  Set Carlo's `sweeps`,
+`thermalization` and `binsize` in units of calls.
+"""
 function Carlo.sweep!(mc::MC, ctx::MCContext)
-    check(ccall((:sse_sweep, libsse), Int32, (Ptr{Cvoid}, Int32, Int32, Int32), mc.hwalkers, 1, is_thermalized(ctx), 0))
+    measure = mc.sweeps_per_call > 1 && is_thermalized(ctx)
+    check(ccall((:sse_sweep, libsse), Int32, (Ptr{Cvoid}, Int32, Int32, Int32), mc.hwalkers, mc.sweeps_per_call, is_thermalized(ctx), measure))
     check(ccall((:sse_sync, libsse), Int32, (Ptr{Cvoid},), mc.hwalkers))
 end
 
-"Carlo.measure! (src/sse.jl:70-87) -> sse_measure; one vector observable (over walkers) per name"
+"Carlo.measure! (src/sse.jl:70-87) -> sse_measure (or, in batched mode, sse_fetch_accumulators); one vector observable (over walkers) per name"
 function Carlo.measure!(mc::MC, ctx::MCContext)
-    out = Matrix{Float64}(undef, mc.nobs, length(mc.T))   # column-major == out[walker][obs] in C
-    check(ccall((:sse_measure, libsse), Int32, (Ptr{Cvoid}, Ptr{Float64}), mc.hwalkers, out))
-    for (i, name) in enumerate(mc.obs_names)
-        name == :WormLengthFraction && any(isnan, @view out[i, :]) && continue
-        measure!(ctx, name, out[i, :])
+    nw = length(mc.T)
+    out = Matrix{Float64}(undef, mc.nobs, nw)   # column-major == out[walker][obs] in C
+    if mc.sweeps_per_call > 1
+        counts = Matrix{Int64}(undef, 2, nw)
+        check(ccall((:sse_fetch_accumulators, libsse), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Int64}, Int32), mc.hwalkers, out, counts, 1))
+        for (i, name) in enumerate(mc.obs_names)
+            c = name == :WormLengthFraction ? (@view counts[2, :]) : (@view counts[1, :])
+            all(>(0), c) || continue
+            measure!(ctx, name, out[i, :] ./ c)
+        end
+    else
+        check(ccall((:sse_measure, libsse), Int32, (Ptr{Cvoid}, Ptr{Float64}), mc.hwalkers, out))
+        for (i, name) in enumerate(mc.obs_names)
+            name == :WormLengthFraction && any(isnan, @view out[i, :]) && continue
+            measure!(ctx, name, out[i, :])
+        end
     end
 end
 
@@ -202,27 +256,35 @@ function Carlo.write_checkpoint(mc::MC, out::HDF5.Group)
     nsites = length(mc.sse_data.sites)
     for w in eachindex(mc.T)
         st = WalkerState(0, 0, 0, C_NULL, 0, C_NULL, 0, 0)
-        ccall((:sse_get_state, libsse), Int32, (Ptr{Cvoid}, Int32, Ref{WalkerState}), mc.hwalkers, w - 1, st)  # query M
+        # size query: with a null buffer the call fills operators_len (= M) and the scalars
+        check(ccall((:sse_get_state, libsse), Int32, (Ptr{Cvoid}, Int32, Ref{WalkerState}), mc.hwalkers, w - 1, st))
         ops = Vector{UInt64}(undef, st.operators_len); state = Vector{UInt8}(undef, nsites)
         GC.@preserve ops state begin
             st.operators = pointer(ops); st.state = pointer(state)
             check(ccall((:sse_get_state, libsse), Int32, (Ptr{Cvoid}, Int32, Ref{WalkerState}), mc.hwalkers, w - 1, st))
         end
-        g = create_group(out, "walker$(w)")
+        # one walker: the reference's own layout (top-level datasets, src/sse.jl:89-97), so either side reads the other's file
+        g = length(mc.T) == 1 ? out : create_group(out, "walker$(w)")
         g["num_operators"] = st.num_operators; g["avg_worm_length"] = st.avg_worm_length
         g["num_worms"] = st.num_worms; g["operators"] = ops; g["state"] = state
         g["rng_draws"] = st.rng_draws; g["T"] = st.T
     end
 end
 
-"Carlo.read_checkpoint (src/sse.jl:99-107) -> sse_set_state per walker"
+"Carlo.read_checkpoint (src/sse.jl:99-107) -> sse_set_state per walker.  A checkpoint written by the reference itself
+(one walker, top-level datasets, `operators` stored as OperCode structs) is accepted: the stream position defaults to 0
+and the temperature to the task's."
 function Carlo.read_checkpoint(mc::MC, in::HDF5.Group)
     for w in eachindex(mc.T)
-        g = in["walker$(w)"]
-        ops = read(g, "operators"); state = read(g, "state")
+        g = (length(mc.T) == 1 && !haskey(in, "walker1")) ? in : in["walker$(w)"]
+        raw = read(g, "operators")
+        ops = eltype(raw) === UInt64 ? raw : collect(reinterpret(UInt64, raw))   # OperCode is a UInt64 wrapper (opercode.jl:33-35)
+        state = UInt8.(read(g, "state"))
+        draws = haskey(g, "rng_draws") ? read(g, "rng_draws") : UInt64(0)
+        T = haskey(g, "T") ? read(g, "T") : mc.T[w]
         GC.@preserve ops state begin
             st = WalkerState(read(g, "num_operators"), read(g, "avg_worm_length"), read(g, "num_worms"), pointer(ops),
-                length(ops), pointer(state), read(g, "rng_draws"), read(g, "T"))
+                length(ops), pointer(state), draws, T)
             check(ccall((:sse_set_state, libsse), Int32, (Ptr{Cvoid}, Int32, Ref{WalkerState}), mc.hwalkers, w - 1, st))
         end
     end
@@ -262,8 +324,51 @@ set_controller!(mc::MC, target_worm_length_fraction::Real, num_worms_attenuation
     check(ccall((:sse_set_controller, libsse), Int32, (Ptr{Cvoid}, Float64, Float64), mc.hwalkers,
                 target_worm_length_fraction, num_worms_attenuation_factor))
 
-"Launch shape of sweep! without a reference counterpart -> sse_set_walkers_per_warp (1, 2 or 4 walkers per warp)."
-set_walkers_per_warp!(mc::MC, k::Integer) =
-    check(ccall((:sse_set_walkers_per_warp, libsse), Int32, (Ptr{Cvoid}, Int32), mc.hwalkers, k))
+"Launch shape of sweep! without a reference counterpart -> sse_set_launch_shape (worm warps: one lane = one walker; stream
+warps: one warp = one walker; 0 = automatic)."
+set_launch_shape!(mc::MC, worm_warps::Integer, stream_warps::Integer) =
+    check(ccall((:sse_set_launch_shape, libsse), Int32, (Ptr{Cvoid}, Int32, Int32), mc.hwalkers, worm_warps, stream_warps))
+
+"Free-running sweeps without a reference counterpart -> sse_advance: every walker does `visit_budget` worm visits (at most
+`max_sweeps` sweeps) and is parked wherever it is; `finish_sweeps!` completes the sweeps in flight (needed before
+measure!/write_checkpoint).  Use for long thermalisations: no walker waits for another one's long worm."
+function advance!(mc::MC, visit_budget::Integer; max_sweeps::Integer = typemax(Int32), thermalized::Bool = false, measure::Bool = false)
+    check(ccall((:sse_advance, libsse), Int32, (Ptr{Cvoid}, Int32, UInt64, Int32, Int32), mc.hwalkers, max_sweeps, visit_budget, thermalized, measure))
+    check(ccall((:sse_sync, libsse), Int32, (Ptr{Cvoid},), mc.hwalkers))
+end
+function finish_sweeps!(mc::MC; thermalized::Bool = false, measure::Bool = false)
+    check(ccall((:sse_finish_sweeps, libsse), Int32, (Ptr{Cvoid}, Int32, Int32), mc.hwalkers, thermalized, measure))
+    check(ccall((:sse_sync, libsse), Int32, (Ptr{Cvoid},), mc.hwalkers))
+end
+
+"One bin summed over the walkers of each group on the device and over the ranks of `comm_init!` by NCCL inside the library
+-> sse_reduce_bins.  `group[w]` in 0:n_groups-1 (e.g. the temperature index).  Returns (sums[nobs, n_groups], counts[2, n_groups])."
+function reduce_bins!(mc::MC, group::Vector{Int32}, n_groups::Integer; reset::Bool = true)
+    sums = Matrix{Float64}(undef, mc.nobs, n_groups); counts = Matrix{Int64}(undef, 2, n_groups)
+    check(ccall((:sse_reduce_bins, libsse), Int32, (Ptr{Cvoid}, Ptr{Int32}, Int32, Ptr{Float64}, Ptr{Int64}, Int32),
+                mc.hwalkers, group, n_groups, sums, counts, reset))
+    return sums, counts
+end
+
+"NCCL communicator for reduce_bins! -> sse_comm_unique_id (rank 0) + sse_comm_init.  Broadcast the id with MPI, e.g.
+`id = MPI.bcast(rank == 0 ? comm_unique_id() : nothing, comm)`."
+function comm_unique_id()
+    id = zeros(UInt8, 128)
+    check(ccall((:sse_comm_unique_id, libsse), Int32, (Ptr{UInt8},), id))
+    return id
+end
+comm_init!(mc::MC, id::Vector{UInt8}, rank::Integer, nranks::Integer) =
+    check(ccall((:sse_comm_init, libsse), Int32, (Ptr{Cvoid}, Ptr{UInt8}, Int32, Int32), mc.hwalkers, id, rank, nranks))
+
+"Replica exchange decided on the device -> sse_pt_set_ladder / sse_pt_exchange (src/sse.jl:390-405 evaluated by a kernel).
+`walker_at_rank`: 0-based walker indices in order of temperature.  Returns the number of accepted pairs; mc.T is refreshed."
+pt_set_ladder!(mc::MC, walker_at_rank::Vector{Int32}) =
+    check(ccall((:sse_pt_set_ladder, libsse), Int32, (Ptr{Cvoid}, Ptr{Int32}, Int32), mc.hwalkers, walker_at_rank, length(walker_at_rank)))
+function pt_exchange!(mc::MC, parity::Integer, seed::Integer, step::Integer)
+    acc = Ref{Int32}(0)
+    check(ccall((:sse_pt_exchange, libsse), Int32, (Ptr{Cvoid}, Int32, UInt64, UInt64, Ref{Int32}), mc.hwalkers, parity, seed, step, acc))
+    check(ccall((:sse_get_temperatures, libsse), Int32, (Ptr{Cvoid}, Ptr{Float64}), mc.hwalkers, mc.T))
+    return acc[]
+end
 
 end # module

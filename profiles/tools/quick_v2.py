@@ -8,8 +8,14 @@ import time
 sys.path.insert(0, ".")
 import numpy as np
 
+import os
+
 import sse_b200 as S
+from sse_b200 import capi
 from sse_b200.walkers import DeviceModel, Walkers
+
+if os.environ.get("SSE_PROBE_LIB"):  # tuning builds of the library (csrc/Makefile `variants`)
+    capi.LIB_PATH = os.path.abspath(os.environ["SSE_PROBE_LIB"])
 
 L, beta, W, dbl, per_level, therm = int(sys.argv[1]), float(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]), int(sys.argv[5]), int(sys.argv[6])
 budget, launches = int(float(sys.argv[7])), int(sys.argv[8])

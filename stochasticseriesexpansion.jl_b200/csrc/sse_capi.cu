@@ -165,7 +165,7 @@ int32_t sweep_shape(const sse_walkers *w, SweepShape &sh) {
     sh.grid = std::min(W, m->n_sm);
     sh.nloc_max = (W + sh.grid - 1) / sh.grid;
     int ww = w->worm_warps > 0 ? w->worm_warps : std::min(8, (sh.nloc_max + 31) / 32);
-    int sw = w->stream_warps > 0 ? w->stream_warps : std::min(SWEEP_MAX_WARPS - ww, std::max(1, std::min(16, sh.nloc_max)));
+    int sw = w->stream_warps > 0 ? w->stream_warps : std::min(SWEEP_MAX_WARPS - ww, std::max(1, sh.nloc_max));
     if (ww < 1 || sw < 1 || ww + sw > SWEEP_MAX_WARPS) return fail("launch shape: need 1 <= worm_warps, 1 <= stream_warps, worm_warps + stream_warps <= 16");
     const int budget = 227 * 1024 - 1024;
     const int fixed = m->dm.tl.bytes + sched_bytes(sh.nloc_max);

@@ -45,8 +45,11 @@ constexpr uint32_t VMASK = ((1u << VBITS) - 1u) << 2;  // bits 2..13
 constexpr int BOND_SHIFT = 2 + VBITS;                  // 14
 constexpr int RNG_WORDS = 66;                          // 33 Philox blocks x 2 draws (see phase_diag_build)
 constexpr int PHASE_WARPS = 4;                         // warps per CTA of sse::k_phase (one warp = one walker)
-constexpr int SWEEP_MAX_WARPS = 16;                    // warps per CTA of sse::k_sweep (launch bounds 512 x 1: 128 registers per thread)
-constexpr int ROT_MARGIN = 128;                        // ring slack kept between the write head and unread old records
+#ifndef SSE_SWEEP_MAX_WARPS
+#define SSE_SWEEP_MAX_WARPS 16
+#endif
+constexpr int SWEEP_MAX_WARPS = SSE_SWEEP_MAX_WARPS;   // warps per CTA of sse::k_sweep (16: launch bounds 512 x 1 = 128 registers per thread)
+constexpr int ROT_MARGIN = 192;                        // ring slack kept between the write head and unread old records
 
 __host__ __device__ __forceinline__ uint32_t op_pack(uint32_t bond, uint32_t gv, uint32_t diag) {
     return 1u | (diag << 1) | (gv << 2) | (bond << BOND_SHIFT);
@@ -145,6 +148,7 @@ struct Ctx {
     uint8_t *state;              // generic pointer: shared memory or the global array
     uint8_t *mark;
     unsigned long long *rng;     // per-warp shared scratch, RNG_WORDS entries
+    uint32_t *queue;             // per-warp shared scratch: 3 x 64 words, operators waiting for the record build
     uint32_t *vfirst, *vlast;
     const unsigned long long *inj;
     long long inj_len;
@@ -267,9 +271,10 @@ __device__ __forceinline__ SmTab stage_tables(const DevModel &dm, uint8_t *smem)
     return st;
 }
 
+constexpr int STREAM_FIXED_BYTES = (((RNG_WORDS * 8) + 15) & ~15) + 3 * 64 * 4;  // draws + build queue
 // bytes of shared scratch of one streaming warp: random draws + (level >= 1) state[N], mark[N] + (level 2) vlast[N]
 __host__ __device__ inline int stream_scratch_bytes(int n_sites, int level) {
-    int b = ((RNG_WORDS * 8) + 15) & ~15;
+    int b = STREAM_FIXED_BYTES;
     if (level >= 1) b += 2 * ((n_sites + 15) & ~15);
     if (level >= 2) b += 4 * ((n_sites + 3) & ~3);
     return b;
@@ -281,9 +286,10 @@ __device__ __forceinline__ Ctx ctx_open(const DevModel &dm, const DevWalkers &dw
     Ctx c;
     c.lane = lane;
     c.rng = reinterpret_cast<unsigned long long *>(scratch);
+    c.queue = reinterpret_cast<uint32_t *>(scratch + (((RNG_WORDS * 8) + 15) & ~15));
     uint8_t *gstate = dw.state + (size_t)w * N;
     if (level) {
-        c.state = scratch + (((RNG_WORDS * 8) + 15) & ~15);
+        c.state = scratch + STREAM_FIXED_BYTES;
         c.mark = c.state + ((N + 15) & ~15);
     } else {
         c.state = gstate;

@@ -33,17 +33,32 @@ __device__ __forceinline__ uint64_t scratch_draw(const Ctx &c, unsigned long lon
 
 // Sequential reader of a walker's operator string: per 32-slot chunk every lane gets the op code of its slot (0 =
 // identity), gathered from the record ring through the occupancy bitmap.  The bitmap words of 32 chunks are held one
-// per lane (the next 32 are already requested), the op codes of the next chunk are requested one step ahead.
+// per lane (the next 32 are already requested); the op codes are requested TWO chunks ahead, because they come from DRAM
+// (measured: with one chunk of lead the pass waits on them, 16 % of its stall samples).
 struct OpReader {
     const uint2 *words;
     const uint4 *rec;
     uint32_t G, Rcap, lane, lt;
     int nchunks;
-    uint32_t wcur, wnext, bits_next, op_next, kold;
+    uint32_t wcur, wnext;       // bitmap words of the block of 32 chunks being requested from, and of the next block
+    uint32_t bits1, op1;        // chunk c+1: occupancy, this lane's op code (requested)
+    uint32_t bits2, op2;        // chunk c+2
+    uint32_t kold, k2;          // first record of chunk c+1 / of chunk c+3
 
     __device__ __forceinline__ uint32_t word_at(int ch) const { return ch < nchunks ? __ldcg(&words[ch].x) : 0u; }
     __device__ __forceinline__ uint32_t op_at(uint32_t bits, uint32_t k0) const {
         return ((bits >> lane) & 1u) ? __ldcg(&rec[ring(G, Rcap, k0 + __popc(bits & lt))].x) : 0u;
+    }
+    // request chunk c (c = 0, 1, 2, ... in order): its occupancy comes from the cached block, its op codes are loaded
+    __device__ __forceinline__ void request(int c, uint32_t &bits, uint32_t &op) {
+        if ((c & 31) == 0 && c > 0) {  // c opens a new block: the old one is used up, the one after is requested
+            wcur = wnext;
+            wnext = word_at(c + 32 + (int)lane);
+        }
+        bits = __shfl_sync(FULL, wcur, c & 31);
+        if (c >= nchunks) bits = 0u;
+        op = op_at(bits, k2);
+        k2 += __popc(bits);
     }
     __device__ __forceinline__ void init(const uint2 *words_, const uint4 *rec_, uint32_t G_, uint32_t Rcap_, int nchunks_,
                                          uint32_t lane_) {
@@ -57,23 +72,20 @@ struct OpReader {
         wcur = word_at((int)lane);
         wnext = word_at(32 + (int)lane);
         kold = 0;
-        bits_next = __shfl_sync(FULL, wcur, 0);
-        op_next = op_at(bits_next, 0);
+        k2 = 0;
+        request(0, bits1, op1);
+        request(1, bits2, op2);
     }
     // chunk ch (called for ch = 0, 1, 2, ... in order): bits = occupancy of its 32 slots, op = this lane's op code;
     // returns the index of the chunk's first record
     __device__ __forceinline__ uint32_t next(int ch, uint32_t &bits, uint32_t &op) {
-        bits = bits_next;
-        op = op_next;
+        bits = bits1;
+        op = op1;
         const uint32_t k0 = kold;
         kold += __popc(bits);
-        if ((ch & 31) == 31) {
-            wcur = wnext;
-            wnext = word_at(ch + 33 + (int)lane);
-        }
-        bits_next = __shfl_sync(FULL, wcur, (ch + 1) & 31);
-        if (ch + 1 >= nchunks) bits_next = 0u;
-        op_next = op_at(bits_next, kold);
+        bits1 = bits2;
+        op1 = op2;
+        request(ch + 2, bits2, op2);
         return k0;
     }
 };
@@ -89,6 +101,78 @@ struct OpReader {
 // (2 draws per identity slot, 1 per diagonal operator, Appendix A), so the draws, the proposed bonds and the bond-table
 // rows of chunk c+1 are fetched (stage B) while chunk c is decided and linked (stage C) from registers and shared memory.
 // ------------------------------------------------------------------------------------------------------
+// make_vertex_list! (src/vertex_list.jl:15-54) for the next `m` <= 32 operators of the new generation, records k0 .. k0+m-1,
+// taken from the warp's queue {op code, site a, site b}: lane i links operator k0 + i.  The diagonal update queues the
+// operators it leaves in the string (about 13 per 32-slot chunk at the BASELINE sizes), so this step runs with all lanes
+// busy instead of once per chunk with most lanes idle.
+constexpr uint32_t BUILD_QUEUE = 64;  // entries; at most 31 waiting + 32 new ones
+
+__device__ __forceinline__ void build_records(const Ctx &c, uint32_t Gn, uint32_t k0, uint32_t m) {
+    const uint32_t lane = c.lane, Rcap = c.Rcap;
+    const bool nn = lane < m;
+    const uint32_t k = k0 + lane, q = k & (BUILD_QUEUE - 1);
+    uint32_t newop = 0, sa = 0, sb = 0;
+    if (nn) {
+        newop = c.queue[q];
+        sa = c.queue[BUILD_QUEUE + q];
+        sb = c.queue[2 * BUILD_QUEUE + q];
+    }
+    // same-site collisions inside the group are rare: every operator tags its two sites, a lost tag
+    // reveals a collision, and only then the nearest earlier / later operator on each site is searched
+    uint32_t pa = NONE24, pb = NONE24, sua = NONE24, sub = NONE24;
+    if (nn) {
+        c.mark[sa] = (uint8_t)lane;
+        c.mark[sb] = (uint8_t)lane;
+    }
+    __syncwarp();
+    const bool lost_a = nn && c.mark[sa] != (uint8_t)lane, lost_b = nn && c.mark[sb] != (uint8_t)lane;
+    if (__ballot_sync(FULL, lost_a || lost_b)) {
+        // losers flag the contested sites; every operator on a flagged site takes part in the search
+        __syncwarp();
+        if (lost_a) c.mark[sa] = 0x7f;
+        if (lost_b) c.mark[sb] = 0x7f;
+        __syncwarp();
+        const bool inv = nn && (c.mark[sa] == 0x7f || c.mark[sb] == 0x7f);
+        for (uint32_t mm = __ballot_sync(FULL, inv); mm;) {
+            const int L = __ffs(mm) - 1;
+            mm &= mm - 1;
+            const uint32_t qa = __shfl_sync(FULL, sa, L), qb = __shfl_sync(FULL, sb, L);
+            const uint32_t qk = (k0 + (uint32_t)L) << 2;
+            if (nn && (int)lane > L) {
+                if (sa == qa) pa = qk | 2u;
+                if (sa == qb) pa = qk | 3u;
+                if (sb == qa) pb = qk | 2u;
+                if (sb == qb) pb = qk | 3u;
+            } else if (nn && (int)lane < L) {
+                if (sua == NONE24) { if (sa == qa) sua = qk; else if (sa == qb) sua = qk | 1u; }
+                if (sub == NONE24) { if (sb == qa) sub = qk; else if (sb == qb) sub = qk | 1u; }
+            }
+        }
+    }
+    uint32_t ma = NONE32, mb = NONE32;
+    if (nn) {
+        if (pa == NONE24) ma = c.vlast[sa];
+        if (pb == NONE24) mb = c.vlast[sb];
+    }
+    __syncwarp();
+    if (nn) {
+        const uint32_t me = k << 2;
+        uint32_t bla = pa, blb = pb;
+        if (pa == NONE24) {
+            if (ma != NONE32) { bla = ma; rec_patch(c.rec, Gn, Rcap, ma, me); }  // vertices[s1,p1] = (s,p) (vertex_list.jl:36-38)
+            else c.vfirst[sa] = me;                                               // vertex_list.jl:40
+        }
+        if (pb == NONE24) {
+            if (mb != NONE32) { blb = mb; rec_patch(c.rec, Gn, Rcap, mb, me | 1u); }
+            else c.vfirst[sb] = me | 1u;
+        }
+        if (sua == NONE24) c.vlast[sa] = me | 2u;  // vertex_list.jl:42
+        if (sub == NONE24) c.vlast[sb] = me | 3u;
+        c.rec[ring(Gn, Rcap, k)] = rec_pack(newop, bla, blb, sua, sub);  // forward links still unknown stay NONE24 until patched
+    }
+    __syncwarp();
+}
+
 struct ChunkIn {  // what stage B hands to stage C
     uint32_t op, bond, idm, dgm, kold0;
     double r;
@@ -157,7 +241,7 @@ __device__ void phase_diag_build(const SmTab &st, const DevModel &dm, const DevW
     const uint32_t Rcap = c.Rcap, n_old = (uint32_t)c.n;
     const uint32_t Gn = ring(c.G, Rcap, n_old);  // the new generation starts right behind the old one
     int n = c.n;
-    uint32_t kbase = 0;
+    uint32_t kbase = 0, built = 0;  // operators of the new generation so far / already linked
     unsigned long long draws = c.draws;
     const int nchunks = (M + 31) >> 5;
     OpReader rd;
@@ -304,70 +388,22 @@ __device__ void phase_diag_build(const SmTab &st, const DevModel &dm, const DevW
             if (is_dg && ((rem >> lane) & 1u)) newop = 0u;
         }
 
-        // ---- records of the new generation ----
+        // ---- the chunk's operators join the queue of the record build (make_vertex_list!) ----
         const bool nn = newop != 0u;
         const uint32_t nm = __ballot_sync(FULL, nn);
         const uint32_t cnt = __popc(nm);
-        const uint32_t k = kbase + __popc(nm & lt);
         // capacity: n_cap records, and the write head must stay clear of old records that are not consumed yet (the
-        // reader is two chunks ahead of this point: ROT_MARGIN covers them)
+        // reader is up to three chunks ahead of this point: ROT_MARGIN covers them)
         if ((long long)kbase + cnt > dw.n_cap ||
             (long long)n_old + kbase + cnt + ROT_MARGIN > (long long)Rcap + in.kold0) {
             c.flags |= SSE_FLAG_N_OVERFLOW;
             return;
         }
-        // same-site collisions inside the chunk are rare: every operator tags its two sites, a lost tag
-        // reveals a collision, and only then the nearest earlier / later operator on each site is searched
-        uint32_t pa = NONE24, pb = NONE24, sua = NONE24, sub = NONE24;
         if (nn) {
-            c.mark[sa] = (uint8_t)lane;
-            c.mark[sb] = (uint8_t)lane;
-        }
-        __syncwarp();
-        const bool lost_a = nn && c.mark[sa] != (uint8_t)lane, lost_b = nn && c.mark[sb] != (uint8_t)lane;
-        if (__ballot_sync(FULL, lost_a || lost_b)) {
-            // losers flag the contested sites; every operator on a flagged site takes part in the search
-            __syncwarp();
-            if (lost_a) c.mark[sa] = 0x7f;
-            if (lost_b) c.mark[sb] = 0x7f;
-            __syncwarp();
-            const bool inv = nn && (c.mark[sa] == 0x7f || c.mark[sb] == 0x7f);
-            for (uint32_t m = __ballot_sync(FULL, inv); m;) {
-                const int L = __ffs(m) - 1;
-                m &= m - 1;
-                const uint32_t qa = __shfl_sync(FULL, sa, L), qb = __shfl_sync(FULL, sb, L);
-                const uint32_t qk = __shfl_sync(FULL, k, L) << 2;
-                if (nn && (int)lane > L) {
-                    if (sa == qa) pa = qk | 2u;
-                    if (sa == qb) pa = qk | 3u;
-                    if (sb == qa) pb = qk | 2u;
-                    if (sb == qb) pb = qk | 3u;
-                } else if (nn && (int)lane < L) {
-                    if (sua == NONE24) { if (sa == qa) sua = qk; else if (sa == qb) sua = qk | 1u; }
-                    if (sub == NONE24) { if (sb == qa) sub = qk; else if (sb == qb) sub = qk | 1u; }
-                }
-            }
-        }
-        uint32_t ma = NONE32, mb = NONE32;
-        if (nn) {
-            if (pa == NONE24) ma = c.vlast[sa];
-            if (pb == NONE24) mb = c.vlast[sb];
-        }
-        __syncwarp();
-        if (nn) {
-            const uint32_t me = k << 2;
-            uint32_t bla = pa, blb = pb;
-            if (pa == NONE24) {
-                if (ma != NONE32) { bla = ma; rec_patch(c.rec, Gn, Rcap, ma, me); }  // vertices[s1,p1] = (s,p) (vertex_list.jl:36-38)
-                else c.vfirst[sa] = me;                                               // vertex_list.jl:40
-            }
-            if (pb == NONE24) {
-                if (mb != NONE32) { blb = mb; rec_patch(c.rec, Gn, Rcap, mb, me | 1u); }
-                else c.vfirst[sb] = me | 1u;
-            }
-            if (sua == NONE24) c.vlast[sa] = me | 2u;  // vertex_list.jl:42
-            if (sub == NONE24) c.vlast[sb] = me | 3u;
-            c.rec[ring(Gn, Rcap, k)] = rec_pack(newop, bla, blb, sua, sub);  // forward links still unknown stay NONE24 until patched
+            const uint32_t q = (kbase + __popc(nm & lt)) & (BUILD_QUEUE - 1);
+            c.queue[q] = newop;
+            c.queue[BUILD_QUEUE + q] = sa;
+            c.queue[2 * BUILD_QUEUE + q] = sb;
         }
         if (lane == (uint32_t)(ch & 31)) wout = make_uint2(nm, kbase);
         if ((ch & 31) == 31 || ch == nchunks - 1) {
@@ -377,6 +413,15 @@ __device__ void phase_diag_build(const SmTab &st, const DevModel &dm, const DevW
         kbase += cnt;
         in = nxt;
         __syncwarp();
+        if (kbase - built >= 32u) {  // 32 operators are waiting: link them with every lane busy
+            build_records(c, Gn, built, 32u);
+            built += 32u;
+        }
+    }
+    while (built < kbase) {
+        const uint32_t m = kbase - built < 32u ? kbase - built : 32u;
+        build_records(c, Gn, built, m);
+        built += m;
     }
     // periodic closure (vertex_list.jl:46-51)
     for (int s = lane; s < N; s += 32) {

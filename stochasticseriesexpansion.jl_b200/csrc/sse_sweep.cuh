@@ -30,7 +30,7 @@ struct SweepStats {
     unsigned long long visits, sweeps, sum_n, sum_M, cyc_build, cyc_finish, cyc_idle, tasks;
 };
 
-// bytes of the scheduler block in shared memory: {n_done, pad x3, status[nloc_max]}
+// bytes of the scheduler block in shared memory: {n_done, n_need, pad x2, status[nloc_max]}
 __host__ __device__ inline int sched_bytes(int nloc_max) { return (16 + 4 * nloc_max + 15) & ~15; }
 
 // One streaming task: whatever walker w needs until it is ready for its worm lane again (or done for this launch).
@@ -98,7 +98,7 @@ __device__ uint32_t stream_task(const SmTab &st, const DevModel &dm, const DevWa
 // Role of a worm warp inside k_sweep: one lane = one walker (walkers j = lane index + m * lanes of the CTA's status table).
 template <bool INJ>
 __device__ __forceinline__ void worm_warp_role(const SmTab &st, const DevModel &dm, const DevWalkers &dw, const SweepArgs &a, uint32_t *n_done,
-                                            uint32_t *status, int nloc, int warp, uint32_t lane) {
+                                            uint32_t *n_need, uint32_t *status, int nloc, int warp, uint32_t lane) {
     // ------------------------------ worm warp: one lane = one walker ------------------------------
     const LaneEnv env = lane_env(st, dm, dw);
     const int nlanes = a.worm_warps * 32, me = warp * 32 + (int)lane;
@@ -159,6 +159,7 @@ __device__ __forceinline__ void worm_warp_role(const SmTab &st, const DevModel &
                 __threadfence();  // op-code stores and the control block before the hand-over
                 st_volatile_shared(status + cur, post);
                 if (post == WS_DONE) atomicAdd(n_done, 1u);
+                else atomicAdd(n_need, 1u);  // WS_NEED_STREAM: wake a stream warp
                 cur = -1;
             }
         }
@@ -181,33 +182,46 @@ __device__ __forceinline__ void worm_warp_role(const SmTab &st, const DevModel &
 // Role of a stream warp inside k_sweep: claim walkers that wait for streaming until every walker of the CTA is done.
 template <bool INJ>
 __device__ __forceinline__ void stream_warp_role(const SmTab &st, const DevModel &dm, const DevWalkers &dw, const SweepArgs &a, uint32_t *n_done,
-                                              uint32_t *status, int nloc, uint8_t *scratch, uint32_t lane) {
+                                              uint32_t *n_need, uint32_t *status, int nloc, uint8_t *scratch, uint32_t lane) {
     // ------------------------------ stream warp: one warp = one walker ------------------------------
     SweepStats ss = {0, 0, 0, 0, 0, 0, 0, 0};
+    unsigned nap = 256;
     while (true) {
-        // claim a walker that waits for streaming: lanes scan the status table, the lowest hit is tried first
+        // claim a walker that waits for streaming.  An idle warp only watches two counters (one lane reads, all agree)
+        // and sleeps with exponential back-off; the status table is scanned only when somebody is waiting.
         int j = -1;
         const long long t0 = clock64();
-        for (int b = 0; b < nloc && j < 0; b += 32) {
-            const int jj = b + (int)lane;
-            const bool want = jj < nloc && ld_volatile_shared(status + jj) == WS_NEED_STREAM;
-            uint32_t m = __ballot_sync(FULL, want);
-            while (m && j < 0) {
-                const int t = __ffs(m) - 1;
-                m &= m - 1;
-                uint32_t got = 0;
-                if ((int)lane == t) got = atomicCAS(status + jj, (uint32_t)WS_NEED_STREAM, (uint32_t)WS_STREAMING) == WS_NEED_STREAM;
-                got = __shfl_sync(FULL, got, t);
-                if (got) j = b + t;
+        uint32_t waiting = 0, done = 0;
+        if (lane == 0) {
+            waiting = ld_volatile_shared(n_need);
+            done = ld_volatile_shared(n_done);
+        }
+        waiting = __shfl_sync(FULL, waiting, 0);
+        done = __shfl_sync(FULL, done, 0);
+        if (waiting) {
+            for (int b = 0; b < nloc && j < 0; b += 32) {
+                const int jj = b + (int)lane;
+                const bool want = jj < nloc && ld_volatile_shared(status + jj) == WS_NEED_STREAM;
+                uint32_t m = __ballot_sync(FULL, want);
+                while (m && j < 0) {  // the lowest hit is tried first
+                    const int t = __ffs(m) - 1;
+                    m &= m - 1;
+                    uint32_t got = 0;
+                    if ((int)lane == t) got = atomicCAS(status + jj, (uint32_t)WS_NEED_STREAM, (uint32_t)WS_STREAMING) == WS_NEED_STREAM;
+                    got = __shfl_sync(FULL, got, t);
+                    if (got) j = b + t;
+                }
             }
         }
         if (j < 0) {
-            // one lane decides for the warp (lanes reading the counter at different times would disagree)
-            if (__shfl_sync(FULL, ld_volatile_shared(n_done), 0) >= (uint32_t)nloc) break;
-            backoff(512);
+            if (done >= (uint32_t)nloc) break;
+            backoff(nap);
+            if (nap < 4096) nap *= 2;
             ss.cyc_idle += (unsigned long long)(clock64() - t0);
             continue;
         }
+        nap = 256;
+        if (lane == 0) atomicSub(n_need, 1u);
         __threadfence();  // the worm lane's writes (op codes, control block) are visible
         const int w = (int)blockIdx.x + j * (int)gridDim.x;
         const uint32_t next = stream_task<INJ>(st, dm, dw, a, w, scratch, lane, ss);
@@ -238,12 +252,13 @@ __global__ void __launch_bounds__(SWEEP_MAX_WARPS * 32, 1) k_sweep(const DevMode
     const SmTab st = stage_tables(dm, smem);
     uint32_t *sched = reinterpret_cast<uint32_t *>(smem + dm.tl.bytes);
     uint32_t *n_done = sched;          // walkers of this CTA that are WS_DONE
+    uint32_t *n_need = sched + 1;      // walkers of this CTA that are WS_NEED_STREAM
     uint32_t *status = sched + 4;
     const int warp = threadIdx.x >> 5;
     const uint32_t lane = threadIdx.x & 31;
     // walkers of this CTA: w = blockIdx.x + j * gridDim.x
     const int nloc = (dw.W - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-    if (threadIdx.x == 0) *n_done = 0;
+    if (threadIdx.x == 0) { *n_done = 0; *n_need = 0; }
     __syncthreads();
     for (int j = threadIdx.x; j < nloc; j += blockDim.x) {
         WalkerCtl *ctl = dw.ctl + ((size_t)blockIdx.x + (size_t)j * gridDim.x);
@@ -259,15 +274,16 @@ __global__ void __launch_bounds__(SWEEP_MAX_WARPS * 32, 1) k_sweep(const DevMode
         else s = ((a.reset ? a.n_sweeps : ctl->sweeps_left) > 0 && a.budget) ? WS_NEED_STREAM : WS_DONE;
         status[j] = s;
         if (s == WS_DONE) atomicAdd(n_done, 1u);
+        if (s == WS_NEED_STREAM) atomicAdd(n_need, 1u);
     }
     __syncthreads();
 
     if (warp < a.worm_warps) {
-        worm_warp_role<INJ>(st, dm, dw, a, n_done, status, nloc, warp, lane);
+        worm_warp_role<INJ>(st, dm, dw, a, n_done, n_need, status, nloc, warp, lane);
     } else if (warp < a.worm_warps + a.stream_warps) {
         uint8_t *scratch = smem + dm.tl.bytes + sched_bytes(a.nloc_max) +
                            (size_t)(warp - a.worm_warps) * stream_scratch_bytes(dm.n_sites, a.level);
-        stream_warp_role<INJ>(st, dm, dw, a, n_done, status, nloc, scratch, lane);
+        stream_warp_role<INJ>(st, dm, dw, a, n_done, n_need, status, nloc, scratch, lane);
     }
 }
 

@@ -191,6 +191,11 @@ static inline unsigned long long atomicOr(unsigned long long *p, unsigned long l
     *p = o | v;
     return o;
 }
+static inline uint32_t atomicSub(uint32_t *p, uint32_t v) {
+    uint32_t o = *p;
+    *p = o - v;
+    return o;
+}
 static inline uint32_t atomicCAS(uint32_t *p, uint32_t cmp, uint32_t v) {
     uint32_t o = *p;
     if (o == cmp) *p = v;

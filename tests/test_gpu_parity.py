@@ -407,6 +407,9 @@ def test_replica_exchange_on_device_walkers():
     rx = ReplicaExchange(gw, seed=1)
     for _ in range(20):
         gw.sweep(3, thermalized=True)
+        with pytest.raises(RuntimeError):
+            rx.step()            # WormLengthFraction samples of these sweeps are still in the bin
+        gw.fetch_accumulators()  # flush: a bin must not span a change of temperature
         T_new = rx.step()
         assert np.allclose(np.sort(T_new), ladder)
     assert rx.proposed > 0 and 0 < rx.accepted <= rx.proposed
