@@ -78,6 +78,13 @@ SSE_HD double sse_u01(uint64_t x) { return (double)(x >> 11) * 0x1.0p-53; }
 /* I(k)-1: uniform integer in 0..k-1 from a raw draw (the reference's 1-based value minus one). */
 SSE_HD uint64_t sse_uint_below(uint64_t x, uint64_t k) { return sse_mulhi64(x, k); }
 
+/* I(k)-1 for k < 2^32, the same value as sse_uint_below with two 32x32 multiplications:
+ * x*k = xh*k*2^32 + xl*k, so its upper 64 bits are (xh*k + (xl*k >> 32)) >> 32 (no carry can be lost: xh*k <= (2^32-1)^2). */
+SSE_HD uint32_t sse_uint_below32(uint64_t x, uint32_t k) {
+    const uint64_t lo = (uint64_t)(uint32_t)x * (uint64_t)k, hi = (x >> 32) * (uint64_t)k;
+    return (uint32_t)((hi + (lo >> 32)) >> 32);
+}
+
 /* exp(y) for y in [-40, 0], plain IEEE arithmetic, identical on host and device. */
 SSE_HD double sse_exp_neg(double y) {
     const double LOG2E = 1.4426950408889634074, LN2_HI = 6.93147180369123816490e-01,

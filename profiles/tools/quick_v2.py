@@ -1,6 +1,8 @@
 """Quick throughput probe of the persistent sweep kernel (no torch): 2D Heisenberg L x L at beta, W walkers, thermalised by
 beta doubling, then timed sse_advance launches of a fixed visit budget per walker.
-usage: quick_v2.py L beta W doublings per_level therm_sweeps budget_visits n_launches [worm_warps stream_warps] [out.jsonl]"""
+usage: quick_v2.py L beta W doublings per_level therm_sweeps budget_visits n_launches [worm_warps stream_warps] [out.jsonl]
+       env SSE_PROBE_SHAPES="ww,sw,level;ww,sw,level;..." times every listed launch shape on the same thermalised batch
+       env SSE_PROBE_LIB=path/to/libsse_b200_wNN.so uses a tuning build of the library"""
 import json
 import sys
 import time
@@ -37,22 +39,29 @@ print(f"setup: doubling {t1 - t0:.1f} s, {therm} sweeps at target {t2 - t1:.1f} 
       f"mean n {c['sum_n'] / max(1, c['sweeps']):.0f}", flush=True)
 wk.advance(budget, thermalized=True)  # de-synchronise the walkers
 wk.fetch_counters(reset=True)
-for i in range(launches):
-    t = time.time()
-    wk.advance(budget, thermalized=True, measure=(i % 2 == 1))
-    dt = time.time() - t
-    c = wk.fetch_counters(reset=True)
-    clk = 1.965e9
-    line = dict(L=L, beta=beta, walkers=W, budget=budget, measure=bool(i % 2), seconds=dt, visits_per_s=c["visits"] / dt,
-                sweeps=c["sweeps"], mean_n=c["sum_n"] / max(1, c["sweeps"]), mean_M=c["sum_M"] / max(1, c["sweeps"]),
-                visits_per_sweep=c["visits"] / max(1, c["sweeps"]),
-                lane_occupancy=c["lane_iters"] / max(1, 32 * c["warp_iters"]),
-                worm_iter_cycles=c["cycles_worm"] / max(1, c["warp_iters"]),
-                stream_busy_warps_per_cta=(c["cycles_build"] + c["cycles_finish"]) / (dt * clk) / min(W, 148),
-                build_cycles_per_task=c["cycles_build"] / max(1, c["tasks"]), finish_cycles_per_task=c["cycles_finish"] / max(1, c["tasks"]),
-                shape=(ww, sw))
-    print(json.dumps(line), flush=True)
-    if out:
-        open(out, "a").write(json.dumps(line) + "\n")
+shapes = [(ww, sw, None)]
+if os.environ.get("SSE_PROBE_SHAPES"):
+    shapes = [tuple(int(x) for x in t.split(",")) for t in os.environ["SSE_PROBE_SHAPES"].split(";")]
+for (sww, ssw, level) in shapes:
+    if level is not None:
+        os.environ["SSE_B200_SMEM_LEVEL"] = str(level)
+    wk.set_launch_shape(sww, ssw)
+    for i in range(launches):
+        t = time.time()
+        wk.advance(budget, thermalized=True, measure=(i % 2 == 1))
+        dt = time.time() - t
+        c = wk.fetch_counters(reset=True)
+        clk = 1.965e9
+        line = dict(L=L, beta=beta, walkers=W, budget=budget, measure=bool(i % 2), seconds=dt, visits_per_s=c["visits"] / dt,
+                    sweeps=c["sweeps"], mean_n=c["sum_n"] / max(1, c["sweeps"]), mean_M=c["sum_M"] / max(1, c["sweeps"]),
+                    visits_per_sweep=c["visits"] / max(1, c["sweeps"]),
+                    lane_occupancy=c["lane_iters"] / max(1, 32 * c["warp_iters"]),
+                    worm_iter_cycles=c["cycles_worm"] / max(1, c["warp_iters"]),
+                    stream_busy_warps_per_cta=(c["cycles_build"] + c["cycles_finish"]) / (dt * clk) / min(W, 148),
+                    build_cycles_per_task=c["cycles_build"] / max(1, c["tasks"]), finish_cycles_per_task=c["cycles_finish"] / max(1, c["tasks"]),
+                    shape=(sww, ssw, level))
+        print(json.dumps(line), flush=True)
+        if out:
+            open(out, "a").write(json.dumps(line) + "\n")
 wk.finish_sweeps(thermalized=True)
 print("flags:", int((wk.get_flags() & 7).sum()), "energy check n*T/N:", float(wk.num_operators().mean() / beta / (L * L)))

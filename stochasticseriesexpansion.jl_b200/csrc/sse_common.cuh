@@ -49,7 +49,7 @@ constexpr int PHASE_WARPS = 4;                         // warps per CTA of sse::
 #define SSE_SWEEP_MAX_WARPS 16
 #endif
 constexpr int SWEEP_MAX_WARPS = SSE_SWEEP_MAX_WARPS;   // warps per CTA of sse::k_sweep (16: launch bounds 512 x 1 = 128 registers per thread)
-constexpr int ROT_MARGIN = 192;                        // ring slack kept between the write head and unread old records
+constexpr int ROT_MARGIN = 224;                        // ring slack between the write head and unread old records (>= 32 * (OP_AHEAD + 2))
 
 __host__ __device__ __forceinline__ uint32_t op_pack(uint32_t bond, uint32_t gv, uint32_t diag) {
     return 1u | (diag << 1) | (gv << 2) | (bond << BOND_SHIFT);
@@ -149,6 +149,7 @@ struct Ctx {
     uint8_t *mark;
     unsigned long long *rng;     // per-warp shared scratch, RNG_WORDS entries
     uint32_t *queue;             // per-warp shared scratch: 3 x 64 words, operators waiting for the record build
+    uint32_t opring_s, biring_s; // shared-space addresses of the warp's prefetch rings (op codes, bond-table rows)
     uint32_t *vfirst, *vlast;
     const unsigned long long *inj;
     long long inj_len;
@@ -190,6 +191,25 @@ __device__ __forceinline__ uint32_t ld_volatile_shared(const uint32_t *p) {
 }
 __device__ __forceinline__ void st_volatile_shared(uint32_t *p, uint32_t v) { *reinterpret_cast<volatile uint32_t *>(p) = v; }
 __device__ __forceinline__ void backoff(unsigned ns) { __nanosleep(ns); }
+// Asynchronous global -> shared copies (LDGSTS) for the prefetch queues of the streaming pass: the data never sits in a
+// register while in flight, so no register move or scoreboard wait can stall on it, and the groups complete in order.
+// pred = false writes zeros without reading.
+__device__ __forceinline__ void cp_async4(uint32_t dst_s, const void *src, bool pred) {
+    const int sz = pred ? 4 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst_s), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst_s, const void *src, bool pred) {
+    const int sz = pred ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_s), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ uint32_t lds32(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
 #endif
 
 // ring position of logical record k of the generation that starts at G
@@ -271,7 +291,11 @@ __device__ __forceinline__ SmTab stage_tables(const DevModel &dm, uint8_t *smem)
     return st;
 }
 
-constexpr int STREAM_FIXED_BYTES = (((RNG_WORDS * 8) + 15) & ~15) + 3 * 64 * 4;  // draws + build queue
+constexpr int OP_AHEAD = 3;              // the streaming pass requests op codes this many chunks ahead of their use
+constexpr int OP_RING = OP_AHEAD + 1;    // chunks of op codes in flight (power of two)
+static_assert((OP_RING & (OP_RING - 1)) == 0, "OP_RING must be a power of two");
+// draws + build queue (3 x 64 words) + op-code ring (OP_RING x 32 words) + bond-row ring (2 x 32 x 16 B)
+constexpr int STREAM_FIXED_BYTES = (((RNG_WORDS * 8) + 15) & ~15) + 3 * 64 * 4 + OP_RING * 32 * 4 + 2 * 32 * 16;
 // bytes of shared scratch of one streaming warp: random draws + (level >= 1) state[N], mark[N] + (level 2) vlast[N]
 __host__ __device__ inline int stream_scratch_bytes(int n_sites, int level) {
     int b = STREAM_FIXED_BYTES;
@@ -287,6 +311,8 @@ __device__ __forceinline__ Ctx ctx_open(const DevModel &dm, const DevWalkers &dw
     c.lane = lane;
     c.rng = reinterpret_cast<unsigned long long *>(scratch);
     c.queue = reinterpret_cast<uint32_t *>(scratch + (((RNG_WORDS * 8) + 15) & ~15));
+    c.opring_s = (uint32_t)__cvta_generic_to_shared(c.queue + 3 * 64);
+    c.biring_s = c.opring_s + OP_RING * 32 * 4;
     uint8_t *gstate = dw.state + (size_t)w * N;
     if (level) {
         c.state = scratch + STREAM_FIXED_BYTES;

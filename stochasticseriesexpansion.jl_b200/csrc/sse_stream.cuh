@@ -33,59 +33,76 @@ __device__ __forceinline__ uint64_t scratch_draw(const Ctx &c, unsigned long lon
 
 // Sequential reader of a walker's operator string: per 32-slot chunk every lane gets the op code of its slot (0 =
 // identity), gathered from the record ring through the occupancy bitmap.  The bitmap words of 32 chunks are held one
-// per lane (the next 32 are already requested); the op codes are requested TWO chunks ahead, because they come from DRAM
-// (measured: with one chunk of lead the pass waits on them, 16 % of its stall samples).
+// per lane (the next 32 are already requested).  The op codes come from DRAM; they are requested OP_AHEAD chunks before
+// their use with asynchronous copies into a small shared-memory ring, one group per chunk (measured with plain loads:
+// the register moves that rotate a software pipeline wait for the load they move, which shortened the lead to one chunk
+// and left the pass waiting on the scoreboard for a quarter of its time).
+// Group accounting: request() leaves the commit to the caller, which commits exactly one op group and `extra` other
+// groups per chunk, in that order; take() waits until the chunk's own group has landed.
+template <int EXTRA>
 struct OpReader {
     const uint2 *words;
     const uint4 *rec;
-    uint32_t G, Rcap, lane, lt;
-    int nchunks;
+    uint32_t G, Rcap, lane, lt, ring_s;
+    int nchunks, next_req;
     uint32_t wcur, wnext;       // bitmap words of the block of 32 chunks being requested from, and of the next block
-    uint32_t bits1, op1;        // chunk c+1: occupancy, this lane's op code (requested)
-    uint32_t bits2, op2;        // chunk c+2
-    uint32_t kold, k2;          // first record of chunk c+1 / of chunk c+3
+    uint32_t kreq;              // first record of the next chunk to request
+    uint32_t kold;              // first record of the next chunk to take
+    uint32_t bits_ring[OP_RING];  // occupancy of the chunks in flight (indexed with unrolled selects: stays in registers)
 
     __device__ __forceinline__ uint32_t word_at(int ch) const { return ch < nchunks ? __ldcg(&words[ch].x) : 0u; }
-    __device__ __forceinline__ uint32_t op_at(uint32_t bits, uint32_t k0) const {
-        return ((bits >> lane) & 1u) ? __ldcg(&rec[ring(G, Rcap, k0 + __popc(bits & lt))].x) : 0u;
-    }
-    // request chunk c (c = 0, 1, 2, ... in order): its occupancy comes from the cached block, its op codes are loaded
-    __device__ __forceinline__ void request(int c, uint32_t &bits, uint32_t &op) {
+    // request the next chunk (chunks are requested in order 0, 1, 2, ...); the caller commits the group
+    __device__ __forceinline__ void request() {
+        const int c = next_req++;
         if ((c & 31) == 0 && c > 0) {  // c opens a new block: the old one is used up, the one after is requested
             wcur = wnext;
             wnext = word_at(c + 32 + (int)lane);
         }
-        bits = __shfl_sync(FULL, wcur, c & 31);
+        uint32_t bits = __shfl_sync(FULL, wcur, c & 31);
         if (c >= nchunks) bits = 0u;
-        op = op_at(bits, k2);
-        k2 += __popc(bits);
+        const bool have = (bits >> lane) & 1u;
+        const uint32_t idx = have ? ring(G, Rcap, kreq + __popc(bits & lt)) : 0u;
+        cp_async4(ring_s + 4u * (32u * (uint32_t)(c & (OP_RING - 1)) + lane), &rec[idx].x, have);
+        kreq += __popc(bits);
+#pragma unroll
+        for (int i = 0; i < OP_RING; ++i)
+            if ((c & (OP_RING - 1)) == i) bits_ring[i] = bits;
     }
     __device__ __forceinline__ void init(const uint2 *words_, const uint4 *rec_, uint32_t G_, uint32_t Rcap_, int nchunks_,
-                                         uint32_t lane_) {
+                                         uint32_t lane_, uint32_t ring_s_) {
         words = words_;
         rec = rec_;
         G = G_;
         Rcap = Rcap_;
         lane = lane_;
         lt = lanemask_lt();
+        ring_s = ring_s_;
         nchunks = nchunks_;
+        next_req = 0;
         wcur = word_at((int)lane);
         wnext = word_at(32 + (int)lane);
+        kreq = 0;
         kold = 0;
-        k2 = 0;
-        request(0, bits1, op1);
-        request(1, bits2, op2);
+#pragma unroll
+        for (int i = 0; i < OP_RING; ++i) bits_ring[i] = 0;
+        for (int i = 0; i < OP_AHEAD; ++i) {  // the pipeline's lead: chunks 0 .. OP_AHEAD-1, with the group pattern of a chunk
+            request();
+            cp_async_commit();
+            for (int e = 0; e < EXTRA; ++e) cp_async_commit();
+        }
     }
-    // chunk ch (called for ch = 0, 1, 2, ... in order): bits = occupancy of its 32 slots, op = this lane's op code;
-    // returns the index of the chunk's first record
-    __device__ __forceinline__ uint32_t next(int ch, uint32_t &bits, uint32_t &op) {
-        bits = bits1;
-        op = op1;
+    // chunk ch (called for ch = 0, 1, 2, ... in order, BEFORE this iteration's request()): bits = occupancy of its 32
+    // slots, op = this lane's op code; returns the index of the chunk's first record
+    __device__ __forceinline__ uint32_t take(int ch, uint32_t &bits, uint32_t &op) {
+        // groups committed after chunk ch's own: EXTRA of its iteration + (OP_AHEAD - 1) later chunks x (1 + EXTRA)
+        cp_async_wait<EXTRA + (OP_AHEAD - 1) * (1 + EXTRA)>();
+        bits = 0;
+#pragma unroll
+        for (int i = 0; i < OP_RING; ++i)
+            if ((ch & (OP_RING - 1)) == i) bits = bits_ring[i];
+        op = lds32(ring_s + 4u * (32u * (uint32_t)(ch & (OP_RING - 1)) + lane));
         const uint32_t k0 = kold;
         kold += __popc(bits);
-        bits1 = bits2;
-        op1 = op2;
-        request(ch + 2, bits2, op2);
         return k0;
     }
 };
@@ -107,85 +124,163 @@ struct OpReader {
 // busy instead of once per chunk with most lanes idle.
 constexpr uint32_t BUILD_QUEUE = 64;  // entries; at most 31 waiting + 32 new ones
 
-__device__ __forceinline__ void build_records(const Ctx &c, uint32_t Gn, uint32_t k0, uint32_t m) {
-    const uint32_t lane = c.lane, Rcap = c.Rcap;
+// Out of line on purpose, like every cold path of this file: the streaming warps of an SM run the same loop at
+// different places, and a loop body beyond the 32 KB instruction cache made instruction fetch the bottleneck of the
+// whole pass (measured: ~1 instruction per cycle and SM however many warps streamed).
+struct BuildArgs {
+    uint32_t *queue;
+    uint8_t *mark;
+    uint32_t *vfirst, *vlast;
+    uint4 *rec;
+    uint32_t Rcap, Gn, lane;
+};
+
+// the nearest earlier / later operator on a contested site, searched among the group's operators (rare)
+__device__ __noinline__ void build_resolve_collisions(uint32_t inv_mask, uint32_t k0, uint32_t lane, bool nn, uint32_t sa, uint32_t sb,
+                                                      uint32_t &pa, uint32_t &pb, uint32_t &sua, uint32_t &sub) {
+    for (uint32_t mm = inv_mask; mm;) {
+        const int L = __ffs(mm) - 1;
+        mm &= mm - 1;
+        const uint32_t qa = __shfl_sync(FULL, sa, L), qb = __shfl_sync(FULL, sb, L);
+        const uint32_t qk = (k0 + (uint32_t)L) << 2;
+        if (nn && (int)lane > L) {
+            if (sa == qa) pa = qk | 2u;
+            if (sa == qb) pa = qk | 3u;
+            if (sb == qa) pb = qk | 2u;
+            if (sb == qb) pb = qk | 3u;
+        } else if (nn && (int)lane < L) {
+            if (sua == NONE24) { if (sa == qa) sua = qk; else if (sa == qb) sua = qk | 1u; }
+            if (sub == NONE24) { if (sb == qa) sub = qk; else if (sb == qb) sub = qk | 1u; }
+        }
+    }
+}
+
+__device__ __noinline__ void build_records(const BuildArgs b, uint32_t k0, uint32_t m) {
+    const uint32_t lane = b.lane, Rcap = b.Rcap, Gn = b.Gn;
     const bool nn = lane < m;
     const uint32_t k = k0 + lane, q = k & (BUILD_QUEUE - 1);
     uint32_t newop = 0, sa = 0, sb = 0;
     if (nn) {
-        newop = c.queue[q];
-        sa = c.queue[BUILD_QUEUE + q];
-        sb = c.queue[2 * BUILD_QUEUE + q];
+        newop = b.queue[q];
+        sa = b.queue[BUILD_QUEUE + q];
+        sb = b.queue[2 * BUILD_QUEUE + q];
     }
     // same-site collisions inside the group are rare: every operator tags its two sites, a lost tag
     // reveals a collision, and only then the nearest earlier / later operator on each site is searched
     uint32_t pa = NONE24, pb = NONE24, sua = NONE24, sub = NONE24;
     if (nn) {
-        c.mark[sa] = (uint8_t)lane;
-        c.mark[sb] = (uint8_t)lane;
+        b.mark[sa] = (uint8_t)lane;
+        b.mark[sb] = (uint8_t)lane;
     }
     __syncwarp();
-    const bool lost_a = nn && c.mark[sa] != (uint8_t)lane, lost_b = nn && c.mark[sb] != (uint8_t)lane;
+    const bool lost_a = nn && b.mark[sa] != (uint8_t)lane, lost_b = nn && b.mark[sb] != (uint8_t)lane;
     if (__ballot_sync(FULL, lost_a || lost_b)) {
         // losers flag the contested sites; every operator on a flagged site takes part in the search
         __syncwarp();
-        if (lost_a) c.mark[sa] = 0x7f;
-        if (lost_b) c.mark[sb] = 0x7f;
+        if (lost_a) b.mark[sa] = 0x7f;
+        if (lost_b) b.mark[sb] = 0x7f;
         __syncwarp();
-        const bool inv = nn && (c.mark[sa] == 0x7f || c.mark[sb] == 0x7f);
-        for (uint32_t mm = __ballot_sync(FULL, inv); mm;) {
-            const int L = __ffs(mm) - 1;
-            mm &= mm - 1;
-            const uint32_t qa = __shfl_sync(FULL, sa, L), qb = __shfl_sync(FULL, sb, L);
-            const uint32_t qk = (k0 + (uint32_t)L) << 2;
-            if (nn && (int)lane > L) {
-                if (sa == qa) pa = qk | 2u;
-                if (sa == qb) pa = qk | 3u;
-                if (sb == qa) pb = qk | 2u;
-                if (sb == qb) pb = qk | 3u;
-            } else if (nn && (int)lane < L) {
-                if (sua == NONE24) { if (sa == qa) sua = qk; else if (sa == qb) sua = qk | 1u; }
-                if (sub == NONE24) { if (sb == qa) sub = qk; else if (sb == qb) sub = qk | 1u; }
-            }
-        }
+        const bool inv = nn && (b.mark[sa] == 0x7f || b.mark[sb] == 0x7f);
+        build_resolve_collisions(__ballot_sync(FULL, inv), k0, lane, nn, sa, sb, pa, pb, sua, sub);
     }
     uint32_t ma = NONE32, mb = NONE32;
     if (nn) {
-        if (pa == NONE24) ma = c.vlast[sa];
-        if (pb == NONE24) mb = c.vlast[sb];
+        if (pa == NONE24) ma = b.vlast[sa];
+        if (pb == NONE24) mb = b.vlast[sb];
     }
     __syncwarp();
     if (nn) {
         const uint32_t me = k << 2;
         uint32_t bla = pa, blb = pb;
         if (pa == NONE24) {
-            if (ma != NONE32) { bla = ma; rec_patch(c.rec, Gn, Rcap, ma, me); }  // vertices[s1,p1] = (s,p) (vertex_list.jl:36-38)
-            else c.vfirst[sa] = me;                                               // vertex_list.jl:40
+            if (ma != NONE32) { bla = ma; rec_patch(b.rec, Gn, Rcap, ma, me); }  // vertices[s1,p1] = (s,p) (vertex_list.jl:36-38)
+            else b.vfirst[sa] = me;                                               // vertex_list.jl:40
         }
         if (pb == NONE24) {
-            if (mb != NONE32) { blb = mb; rec_patch(c.rec, Gn, Rcap, mb, me | 1u); }
-            else c.vfirst[sb] = me | 1u;
+            if (mb != NONE32) { blb = mb; rec_patch(b.rec, Gn, Rcap, mb, me | 1u); }
+            else b.vfirst[sb] = me | 1u;
         }
-        if (sua == NONE24) c.vlast[sa] = me | 2u;  // vertex_list.jl:42
-        if (sub == NONE24) c.vlast[sb] = me | 3u;
-        c.rec[ring(Gn, Rcap, k)] = rec_pack(newop, bla, blb, sua, sub);  // forward links still unknown stay NONE24 until patched
+        if (sua == NONE24) b.vlast[sa] = me | 2u;  // vertex_list.jl:42
+        if (sub == NONE24) b.vlast[sb] = me | 3u;
+        b.rec[ring(Gn, Rcap, k)] = rec_pack(newop, bla, blb, sua, sub);  // forward links still unknown stay NONE24 until patched
     }
     __syncwarp();
 }
 
-struct ChunkIn {  // what stage B hands to stage C
+// The in-order recurrence of the accept tests (sse.jl:164-166,176-178) for a chunk in which the bound test left some lane
+// undecided: lane l only depends on lanes < l, so after i rounds the first i lanes are final (rare: ~600/(M-n) per chunk).
+__device__ __noinline__ void diag_resolve_exact(int n, int M, double p_make_bond_raw, double p_remove_bond_raw, bool is_id, bool is_dg,
+                                                double r, double w, uint32_t lt, uint32_t &ins, uint32_t &rem) {
+    ins = 0;
+    rem = 0;
+    while (true) {
+        const int nl = n + __popc(ins & lt) - __popc(rem & lt);
+        bool a2 = false;
+        if (is_id) {
+            const double p_make_bond = p_make_bond_raw / (double)(M - nl);  // sse.jl:164
+            a2 = r < p_make_bond * w;                                        // sse.jl:166
+        } else if (is_dg) {
+            const double p_remove_bond = (double)(M - nl + 1) * p_remove_bond_raw;  // sse.jl:176-177
+            a2 = r * w < p_remove_bond;                                              // sse.jl:178
+        }
+        const uint32_t ins2 = __ballot_sync(FULL, is_id && a2), rem2 = __ballot_sync(FULL, is_dg && a2);
+        if (ins2 == ins && rem2 == rem) break;
+        ins = ins2;
+        rem = rem2;
+    }
+}
+
+// accept thresholds for an operator count anywhere in [lo, hi] (two divisions; recomputed every few chunks)
+__device__ __noinline__ void diag_window(int M, int lo, int hi, double p_make_bond_raw, double p_remove_bond_raw, double &pm_lo,
+                                         double &pm_hi, double &rm_sure, double &rm_maybe) {
+    pm_lo = p_make_bond_raw / (double)(M - lo);
+    pm_hi = (M - hi > 0) ? p_make_bond_raw / (double)(M - hi) : __longlong_as_double(0x7ff0000000000000ll);
+    rm_sure = (double)(M - hi + 1) * p_remove_bond_raw;
+    rm_maybe = (double)(M - lo + 1) * p_remove_bond_raw;
+}
+
+// state seen by identity lanes / state written by off-diagonal lanes when operators of one chunk share sites (rare)
+__device__ __noinline__ void diag_resolve_state(uint32_t offm, uint32_t lane, bool is_id, bool is_off, uint32_t sa, uint32_t sb, uint32_t ta,
+                                                uint32_t tb, uint32_t &s_a, uint32_t &s_b, bool &wa, bool &wb) {
+    for (uint32_t m = offm; m;) {
+        const int L = __ffs(m) - 1;
+        m &= m - 1;
+        const uint32_t qa = __shfl_sync(FULL, sa, L), qb = __shfl_sync(FULL, sb, L);
+        const uint32_t qta = __shfl_sync(FULL, ta, L), qtb = __shfl_sync(FULL, tb, L);
+        if (is_id && (int)lane > L) {
+            if (sa == qa) s_a = qta;
+            if (sa == qb) s_a = qtb;
+            if (sb == qa) s_b = qta;
+            if (sb == qb) s_b = qtb;
+        }
+        if (is_off && (int)lane < L) {  // a later operator of the chunk overwrites this site
+            if (sa == qa || sa == qb) wa = false;
+            if (sb == qa || sb == qb) wb = false;
+        }
+    }
+}
+
+// one more Philox block behind the 32 a chunk's lanes computed (needed when 64 draws start at an odd stream position)
+__device__ __noinline__ void philox_extra_block(unsigned long long seed, unsigned long long wid, unsigned long long j, uint4 *dst) {
+    uint32_t b[4];
+    sse_philox_block(seed, wid, j, b);
+    *dst = make_uint4(b[0], b[1], b[2], b[3]);
+}
+
+struct ChunkIn {  // what stage B hands to stage C (the bond-table rows go through shared memory)
     uint32_t op, bond, idm, dgm, kold0;
     double r;
-    uint4 bi;
 };
 
 template <bool INJ>
-__device__ __forceinline__ ChunkIn diag_stage_b(const DevModel &dm, const Ctx &c, OpReader &rd, int ch, int M, bool do_diag,
+__device__ __forceinline__ ChunkIn diag_stage_b(const DevModel &dm, const Ctx &c, OpReader<1> &rd, int ch, int M, bool do_diag,
                                                 unsigned long long &draws) {
     const uint32_t lane = c.lane, lt = rd.lt;
     ChunkIn in;
     uint32_t obits;
-    in.kold0 = rd.next(ch, obits, in.op);
+    in.kold0 = rd.take(ch, obits, in.op);
+    rd.request();  // op codes of chunk ch + OP_AHEAD
+    cp_async_commit();
     const int p = ch * 32 + (int)lane;
     const bool nonid = in.op != 0u;
     const bool is_id = (p < M) && !nonid;
@@ -203,14 +298,11 @@ __device__ __forceinline__ ChunkIn diag_stage_b(const DevModel &dm, const Ctx &c
             const unsigned long long my = draws + 2u * __popc(in.idm & lt) + __popc(in.dgm & lt);
             const unsigned long long j0 = draws >> 1;
             fill_draws<INJ>(c, j0);
-            if (!INJ && (draws & 1ull) && D == 64u && lane == 0) {  // the one draw beyond 32 blocks
-                uint32_t b[4];
-                sse_philox_block(c.seed, c.wid, j0 + 32, b);
-                reinterpret_cast<uint4 *>(c.rng)[32] = make_uint4(b[0], b[1], b[2], b[3]);
-            }
+            if (!INJ && (draws & 1ull) && D == 64u && lane == 0)  // the one draw beyond 32 blocks
+                philox_extra_block(c.seed, c.wid, j0 + 32, reinterpret_cast<uint4 *>(c.rng) + 32);
             __syncwarp();
             if (is_id) {
-                in.bond = (uint32_t)sse_uint_below(scratch_draw<INJ>(c, j0, my), (uint64_t)dm.n_bonds);  // rand(rng, 1:N_b) - 1 (sse.jl:152)
+                in.bond = sse_uint_below32(scratch_draw<INJ>(c, j0, my), (uint32_t)dm.n_bonds);  // rand(rng, 1:N_b) - 1 (sse.jl:152)
                 in.r = sse_u01(scratch_draw<INJ>(c, j0, my + 1));                                         // sse.jl:166
             } else if (is_dg) {
                 in.r = sse_u01(scratch_draw<INJ>(c, j0, my));                                             // sse.jl:178
@@ -219,8 +311,9 @@ __device__ __forceinline__ ChunkIn diag_stage_b(const DevModel &dm, const Ctx &c
             __syncwarp();  // the scratch is refilled for the next chunk
         }
     }
-    in.bi = make_uint4(0, 0, 0, 0);
-    if (is_id || nonid) in.bi = __ldg(dm.bond_info + in.bond);
+    // the chunk's bond-table rows travel to shared memory while the previous chunk is decided (stage C)
+    cp_async16(c.biring_s + 16u * (32u * (uint32_t)(ch & 1) + lane), dm.bond_info + in.bond, is_id || nonid);
+    cp_async_commit();
     return in;
 }
 
@@ -244,17 +337,37 @@ __device__ void phase_diag_build(const SmTab &st, const DevModel &dm, const DevW
     uint32_t kbase = 0, built = 0;  // operators of the new generation so far / already linked
     unsigned long long draws = c.draws;
     const int nchunks = (M + 31) >> 5;
-    OpReader rd;
-    rd.init(c.words, c.rec, c.G, Rcap, nchunks, lane);
+    OpReader<1> rd;
+    rd.init(c.words, c.rec, c.G, Rcap, nchunks, lane, c.opring_s);
     uint2 wout = make_uint2(0u, 0u);  // new {bits, rank} of chunk 32*j + lane, written 32 words at a time
     // accept thresholds (see below), valid while the operator count stays inside [win_lo, win_hi]
     int win_lo = 1, win_hi = 0;
     double pm_lo = 0, pm_hi = 0, rm_sure = 0, rm_maybe = 0;
 
-    ChunkIn in = diag_stage_b<INJ>(dm, c, rd, 0, M, do_diag, draws);
-    for (int ch = 0; ch < nchunks; ++ch) {
-        ChunkIn nxt = in;
-        if (ch + 1 < nchunks) nxt = diag_stage_b<INJ>(dm, c, rd, ch + 1, M, do_diag, draws);  // stage B of the next chunk
+    BuildArgs ba;
+    ba.queue = c.queue;
+    ba.mark = c.mark;
+    ba.vfirst = c.vfirst;
+    ba.vlast = c.vlast;
+    ba.rec = c.rec;
+    ba.Rcap = Rcap;
+    ba.Gn = Gn;
+    ba.lane = lane;
+    ChunkIn in, nxt;
+    in.op = in.bond = in.idm = in.dgm = in.kold0 = 0;
+    in.r = 0.0;
+    nxt = in;
+    for (int ch = -1; ch < nchunks; ++ch) {  // iteration ch: stage B of chunk ch + 1, then stage C of chunk ch
+        if (ch + 1 < nchunks) {
+            nxt = diag_stage_b<INJ>(dm, c, rd, ch + 1, M, do_diag, draws);
+        } else {  // no chunk left to prepare: keep the group pattern of an iteration
+            cp_async_commit();
+            cp_async_commit();
+        }
+        if (ch < 0) {
+            in = nxt;
+            continue;
+        }
         // ------------------------------ stage C of chunk ch ------------------------------
         const int p = ch * 32 + (int)lane;
         const bool active = p < M;
@@ -265,7 +378,8 @@ __device__ void phase_diag_build(const SmTab &st, const DevModel &dm, const DevW
         const bool is_off = nonid && !(op & 2u);
         const uint32_t bond = in.bond, gv = op_gv(op), idm = in.idm, dgm = in.dgm;
         const double r = in.r;
-        const uint4 bi = in.bi;
+        cp_async_wait<2>();  // this chunk's bond rows have landed; the two groups of stage B above may still be in flight
+        const uint4 bi = lds128(c.biring_s + 16u * (32u * (uint32_t)(ch & 1) + lane));
         const uint32_t sa = bi.x & NONE24, sb = bi.y & NONE24;
         uint32_t newop = op;
 
@@ -296,24 +410,7 @@ __device__ void phase_diag_build(const SmTab &st, const DevModel &dm, const DevW
                 const uint32_t anyhit = __ballot_sync(FULL, hit);
                 __syncwarp();
                 bool wa = is_off, wb = is_off;
-                if (anyhit) {
-                    for (uint32_t m = offm; m;) {
-                        const int L = __ffs(m) - 1;
-                        m &= m - 1;
-                        const uint32_t qa = __shfl_sync(FULL, sa, L), qb = __shfl_sync(FULL, sb, L);
-                        const uint32_t qta = __shfl_sync(FULL, ta, L), qtb = __shfl_sync(FULL, tb, L);
-                        if (is_id && (int)lane > L) {
-                            if (sa == qa) s_a = qta;
-                            if (sa == qb) s_a = qtb;
-                            if (sb == qa) s_b = qta;
-                            if (sb == qb) s_b = qtb;
-                        }
-                        if (is_off && (int)lane < L) {  // a later operator of the chunk overwrites this site
-                            if (sa == qa || sa == qb) wa = false;
-                            if (sb == qa || sb == qb) wb = false;
-                        }
-                    }
-                }
+                if (anyhit) diag_resolve_state(offm, lane, is_id, is_off, sa, sb, ta, tb, s_a, s_b, wa, wb);
                 if (is_off) {
                     if (wa) c.state[sa] = (uint8_t)ta;
                     if (wb) c.state[sb] = (uint8_t)tb;
@@ -345,10 +442,7 @@ __device__ void phase_diag_build(const SmTab &st, const DevModel &dm, const DevW
             if (n_lo < win_lo || n_hi > win_hi) {
                 win_lo = n_lo - 256;
                 win_hi = n_hi + 256;
-                pm_lo = p_make_bond_raw / (double)(M - win_lo);
-                pm_hi = (M - win_hi > 0) ? p_make_bond_raw / (double)(M - win_hi) : __longlong_as_double(0x7ff0000000000000ll);
-                rm_sure = (double)(M - win_hi + 1) * p_remove_bond_raw;
-                rm_maybe = (double)(M - win_lo + 1) * p_remove_bond_raw;
+                diag_window(M, win_lo, win_hi, p_make_bond_raw, p_remove_bond_raw, pm_lo, pm_hi, rm_sure, rm_maybe);
             }
             bool acc = false, amb = false;
             if (is_id) {
@@ -361,24 +455,7 @@ __device__ void phase_diag_build(const SmTab &st, const DevModel &dm, const DevW
             }
             uint32_t ins, rem;
             if (__ballot_sync(FULL, amb)) {
-                // lane l only depends on lanes < l: after i rounds the first i lanes are final
-                ins = 0;
-                rem = 0;
-                while (true) {
-                    const int nl = n + __popc(ins & lt) - __popc(rem & lt);
-                    bool a2 = false;
-                    if (is_id) {
-                        const double p_make_bond = p_make_bond_raw / (double)(M - nl);  // sse.jl:164
-                        a2 = r < p_make_bond * w;                                        // sse.jl:166
-                    } else if (is_dg) {
-                        const double p_remove_bond = (double)(M - nl + 1) * p_remove_bond_raw;  // sse.jl:176-177
-                        a2 = r * w < p_remove_bond;                                              // sse.jl:178
-                    }
-                    const uint32_t ins2 = __ballot_sync(FULL, is_id && a2), rem2 = __ballot_sync(FULL, is_dg && a2);
-                    if (ins2 == ins && rem2 == rem) break;
-                    ins = ins2;
-                    rem = rem2;
-                }
+                diag_resolve_exact(n, M, p_make_bond_raw, p_remove_bond_raw, is_id, is_dg, r, w, lt, ins, rem);
             } else {
                 ins = __ballot_sync(FULL, is_id && acc);
                 rem = __ballot_sync(FULL, is_dg && acc);
@@ -393,7 +470,7 @@ __device__ void phase_diag_build(const SmTab &st, const DevModel &dm, const DevW
         const uint32_t nm = __ballot_sync(FULL, nn);
         const uint32_t cnt = __popc(nm);
         // capacity: n_cap records, and the write head must stay clear of old records that are not consumed yet (the
-        // reader is up to three chunks ahead of this point: ROT_MARGIN covers them)
+        // reader is up to OP_AHEAD + 2 chunks ahead of this point: ROT_MARGIN covers them)
         if ((long long)kbase + cnt > dw.n_cap ||
             (long long)n_old + kbase + cnt + ROT_MARGIN > (long long)Rcap + in.kold0) {
             c.flags |= SSE_FLAG_N_OVERFLOW;
@@ -414,13 +491,13 @@ __device__ void phase_diag_build(const SmTab &st, const DevModel &dm, const DevW
         in = nxt;
         __syncwarp();
         if (kbase - built >= 32u) {  // 32 operators are waiting: link them with every lane busy
-            build_records(c, Gn, built, 32u);
+            build_records(ba, built, 32u);
             built += 32u;
         }
     }
     while (built < kbase) {
         const uint32_t m = kbase - built < 32u ? kbase - built : 32u;
-        build_records(c, Gn, built, m);
+        build_records(ba, built, m);
         built += m;
     }
     // periodic closure (vertex_list.jl:46-51)
@@ -516,11 +593,13 @@ __device__ void phase_measure(const SmTab &st, const DevModel &dm, const DevWalk
             if (lane == 0) { mag[g] = tmpmag[g]; absmag[g] = fabs(tmpmag[g]); mag2[g] = tmpmag[g] * tmpmag[g]; mag4[g] = mag2[g] * mag2[g]; }
         }
         uint32_t neg = 0;
-        OpReader rd;
-        rd.init(c.words, c.rec, c.G, c.Rcap, nchunks, lane);
+        OpReader<0> rd;
+        rd.init(c.words, c.rec, c.G, c.Rcap, nchunks, lane, c.opring_s);
         for (int ch = 0; ch < nchunks; ++ch) {
             uint32_t bits, op;
-            rd.next(ch, bits, op);
+            rd.take(ch, bits, op);
+            rd.request();
+            cp_async_commit();
             const bool nonid = op != 0u;
             if (e0 == 0) neg += __popc(__ballot_sync(FULL, nonid && st.vneg[op_gv(op)]));  // measure_sign (sse.jl:305-314)
             if (ne == 0) continue;

@@ -277,6 +277,27 @@ static inline void st_volatile_shared(uint32_t *p, uint32_t v) {
     *reinterpret_cast<volatile uint32_t *>(p) = v;
 }
 static inline void backoff(unsigned) { emu::poll_yield(); }
+// asynchronous copies: performed at once (one legal timing); pred = false zero-fills
+static inline void cp_async4(uint32_t dst_s, const void *src, bool pred) {
+    uint32_t v = 0;
+    if (pred) {
+        emu_check_global(src, 4);
+        v = *reinterpret_cast<const uint32_t *>(src);
+    }
+    *reinterpret_cast<uint32_t *>(emu_smem_at(dst_s, 4)) = v;
+}
+static inline void cp_async16(uint32_t dst_s, const void *src, bool pred) {
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (pred) {
+        emu_check_global(src, 16);
+        v = *reinterpret_cast<const uint4 *>(src);
+    }
+    *reinterpret_cast<uint4 *>(emu_smem_at(dst_s, 16)) = v;
+}
+static inline void cp_async_commit() {}
+template <int N>
+static inline void cp_async_wait() {}
+static inline uint32_t lds32(uint32_t a) { return *reinterpret_cast<const uint32_t *>(emu_smem_at(a, 4)); }
 }  // namespace sse
 
 // ---- CUDA runtime stand-ins (host "device memory" = malloc with red zones) ------------------------------

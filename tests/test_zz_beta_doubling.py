@@ -175,31 +175,33 @@ def _oracle_thermalize_by_doubling(om, T, seed, wid, doublings, per_level, final
     return fw
 
 
-def _body_full_size_parity(L, beta, doublings, shape=(0, 0), model=None, per_level=4, n_factor=0.75):
-    """BASELINE.json configs[1] geometry at full size (2D Heisenberg, L = beta = 32: M ~ 1e5 slots, n ~ 4.6e4 records, worms
-    of ~1e4 visits): thousands of 32-slot chunks per sweep, 18-bit links, hundreds of draw refills per worm —
-    bit for bit against the oracle, reached by beta doubling."""
+def _body_full_size_parity(L, beta, doublings, shape=(0, 0), model=None, per_level=4, n_est=None, walkers=3):
+    """BASELINE.json geometries at full size, a few walkers each, reached by beta doubling, bit for bit against the oracle
+    (strings of 1e5 - 1e6 slots: thousands of 32-slot chunks per sweep, 20-bit links, the record ring wrapping around every
+    few sweeps, worms of 1e4 - 1e5 visits).  Default model: 2D Heisenberg (configs[1] at L = beta = 32, configs[2] at 64)."""
     from helpers import heisenberg_square
 
-    model = heisenberg_square(L, False, measure=("magnetization",))
+    if model is None:
+        model = heisenberg_square(L, False, measure=("magnetization",))
+        n_est = 0.75 * beta * 2 * L * L
     dm, om = _pair(model)
-    W = 3
+    W = walkers
     T = 1.0 / beta
-    n_est = 0.75 * beta * 2 * L * L
-    gw = Walkers(dm, np.full(W, T), m_capacity=int(3.6 * n_est), n_capacity=int(1.7 * n_est), seed=77)
+    gw = Walkers(dm, np.full(W, T), m_capacity=int(3.6 * n_est), n_capacity=int(1.25 * n_est), seed=77)
     gw.set_launch_shape(*shape)
-    gw.thermalize_by_beta_doubling(doublings, sweeps_per_level=4, final_sweeps=2)
+    gw.thermalize_by_beta_doubling(doublings, sweeps_per_level=per_level, final_sweeps=2)
     gw.sweep(2, thermalized=True, measure=True)
     sums, counts = gw.fetch_accumulators()
     for i in range(W):
-        fw = _oracle_thermalize_by_doubling(om, T, 77, i, doublings, 4, 2)
+        fw = _oracle_thermalize_by_doubling(om, T, 77, i, doublings, per_level, 2)
         fw.sweep(2, thermalized=True, measure=True)
         a, b = gw.get_state(i), fw.get_state()
         _same_state(a, b, f"full size walker {i}")
         osums, ocounts = fw.fetch_accumulators()
         assert np.array_equal(counts[i], ocounts)
         np.testing.assert_allclose(sums[i], osums, rtol=1e-12, atol=1e-300)
-    assert gw.num_operators().min() > 0.6 * beta * 2 * L * L  # really at full size
+    assert gw.num_operators().min() > 0.5 * n_est  # really at full size
+    return gw
 
 
 def test_emu_full_size_parity(emu):
@@ -217,3 +219,65 @@ def test_emu_full_size_parity(emu):
 @pytest.mark.parametrize("shape", [(0, 0), (1, 3)])
 def test_gpu_full_size_parity(shape):
     _body_full_size_parity(32, 32, 5, shape)
+
+
+@pytest.mark.gpu
+def test_gpu_full_size_parity_config2():
+    """BASELINE.json configs[2]: L = beta = 64 (4096 sites, n ~ 3.7e5 records, M ~ 9e5 slots, ~8.7e5 worm visits per sweep)."""
+    gw = _body_full_size_parity(64, 64, 6)
+    assert gw.num_operators().min() > 3.5e5
+
+
+@pytest.mark.gpu
+def test_gpu_full_size_parity_config4():
+    """BASELINE.json configs[4]: fully frustrated bilayer in the dimer basis (ClusterModel, dims (4,4), three worm types,
+    36-vertex tables with up to 3 outcomes per transition), L = 48, beta = 48 — test/test_jobs.jl:139-167 scaled up."""
+    from helpers import dimer_bilayer
+
+    L, beta = 48, 48
+    model = dimer_bilayer(L)
+    # <n> ~ beta * sum_b <W_b>: measured on the oracle at small L, ~1.45 operators per bond and unit of beta
+    _body_full_size_parity(L, beta, 5, model=model, n_est=1.6 * beta * 2 * L * L, per_level=3, walkers=2)
+
+
+def _body_bani_cold_task(L, T, walkers, sweeps, budget):
+    """BASELINE.json configs[3]: the coldest BaNi2V2O8 task (examples/bani2v2o8.jl:12-31: S = 1 honeycomb with single-ion
+    anisotropy, T = 0.05) from the reference's own cold start, UNSCREENED seeds: sse_advance gives every walker the same
+    number of worm visits per launch, so a walker inside a very long early worm delays nobody, and whoever has finished
+    its sweeps matches the oracle bit for bit."""
+    from helpers import bani_honeycomb
+
+    model = bani_honeycomb(L)
+    dm, om = _pair(model)
+    n_est = 2.2 * (1.0 / T) * 3 * L * L  # ~2 operators per bond and unit of beta (golden OperatorCount: 65 316 at L = 20)
+    gw = Walkers(dm, np.full(walkers, T), m_capacity=int(4 * n_est) + 4096, n_capacity=int(1.3 * n_est) + 1024, seed=1234)
+    gw.init()
+    launches = 0
+    while True:
+        gw.advance(budget, thermalized=False)  # free-running: nobody waits for anybody
+        launches += 1
+        done, in_flight = gw.progress()
+        if done.min() >= sweeps:
+            break
+        assert launches < 2000, (done.min(), done.max())
+    gw.finish_sweeps(thermalized=False)
+    done, in_flight = gw.progress()
+    assert not in_flight.any()
+    order = np.argsort(done)
+    for i in list(order[:2]) + list(order[-2:]):  # the two slowest and the two fastest walkers
+        ow = OracleWalker(om, T, seed=1234, walker_id=int(i))
+        ow.init()
+        ow.sweep(int(done[i]), thermalized=False)
+        _same_state(gw.get_state(int(i)), ow.get_state(), f"bani L={L} T={T} walker {i} after {done[i]} sweeps")
+    return done, launches
+
+
+def test_emu_bani_cold_task(emu):
+    done, launches = _body_bani_cold_task(3, 0.05, 5, 12, 20000)
+    assert done.min() >= 12 and launches > 1
+
+
+@pytest.mark.gpu
+def test_gpu_bani_cold_task():
+    done, launches = _body_bani_cold_task(20, 0.05, 64, 40, 3_000_000)
+    assert done.min() >= 40
