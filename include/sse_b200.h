@@ -201,6 +201,9 @@ int32_t sse_fetch_counters(sse_walkers *w, uint64_t out[SSE_N_COUNTERS], int32_t
 
 /* Carlo.write_checkpoint / read_checkpoint (src/sse.jl:89-107). */
 int32_t sse_get_state(sse_walkers *w, int32_t walker, sse_walker_state *st);
+/* The same for walkers first .. first+count-1 with one round of device-to-host copies (states[count]); a call with
+ * NULL buffers fills the sizes (operators_len = M) and the scalars only. */
+int32_t sse_get_states(sse_walkers *w, int32_t first, int32_t count, sse_walker_state *states);
 int32_t sse_set_state(sse_walkers *w, int32_t walker, const sse_walker_state *st);
 int32_t sse_get_flags(sse_walkers *w, uint32_t *flags /* [n_walkers] */);
 

@@ -803,38 +803,66 @@ int32_t download_string(sse_walkers *w, int i, const WalkerCtl &c, std::vector<u
 
 }  // namespace
 
+// Carlo.write_checkpoint for a range of walkers with ONE round of copies: the control blocks come down first (sizes),
+// then every walker's bitmap words, ring segments and state are queued on the stream and awaited together.
+int32_t sse_get_states(sse_walkers *w, int32_t first, int32_t count, sse_walker_state *sts) {
+    if (!w || !sts) return fail("null argument");
+    if (first < 0 || count < 0 || first + count > w->dw.W) return fail("sse_get_states: walker range out of bounds");
+    if (count == 0) return 0;
+    if (int32_t s = require_between_sweeps(w, "sse_get_state")) return s;
+    const sse_model *m = w->model;
+    const int N = m->dm.n_sites;
+    std::vector<WalkerCtl> ctl(count);
+    CU(cudaMemcpyAsync(ctl.data(), w->dw.ctl + first, sizeof(WalkerCtl) * count, cudaMemcpyDeviceToHost, w->stream));
+    CU(cudaStreamSynchronize(w->stream));
+    std::vector<std::vector<uint2>> words(count);
+    std::vector<std::vector<uint4>> rec(count);
+    for (int j = 0; j < count; ++j) {
+        const WalkerCtl &c = ctl[j];
+        sse_walker_state *st = sts + j;
+        st->num_operators = c.n;
+        st->rng_draws = c.draws;
+        st->avg_worm_length = c.avg_wl;
+        st->num_worms = c.num_worms;
+        st->T = c.T;
+        if (st->operators) {
+            if (st->operators_len < c.M) {
+                st->operators_len = c.M;
+                return fail("sse_get_state: operators buffer too small (walker " + std::to_string(first + j) + ")");
+            }
+            const int i = first + j, nw = (c.M + 31) / 32;
+            words[j].resize(nw);
+            rec[j].resize(c.n);
+            if (nw) CU(cudaMemcpyAsync(words[j].data(), w->dw.words + (size_t)i * w->dw.Mw_cap, sizeof(uint2) * nw, cudaMemcpyDeviceToHost, w->stream));
+            const uint4 *ring0 = w->dw.rec + (size_t)i * w->dw.R_cap;
+            const int64_t head = std::min<int64_t>(c.n, w->dw.R_cap - c.G);
+            if (head > 0) CU(cudaMemcpyAsync(rec[j].data(), ring0 + c.G, sizeof(uint4) * head, cudaMemcpyDeviceToHost, w->stream));
+            if (c.n > head) CU(cudaMemcpyAsync(rec[j].data() + head, ring0, sizeof(uint4) * (c.n - head), cudaMemcpyDeviceToHost, w->stream));
+        }
+        if (st->state) CU(cudaMemcpyAsync(st->state, w->dw.state + (size_t)(first + j) * N, N, cudaMemcpyDeviceToHost, w->stream));
+    }
+    CU(cudaStreamSynchronize(w->stream));
+    for (int j = 0; j < count; ++j) {
+        const WalkerCtl &c = ctl[j];
+        sse_walker_state *st = sts + j;
+        if (st->operators) {
+            int64_t k = 0;
+            for (int p = 0; p < c.M; ++p) {
+                if (!((words[j][p >> 5].x >> (p & 31)) & 1u)) { st->operators[p] = 0; continue; }
+                if (k >= c.n) return fail("sse_get_state: corrupt occupancy bitmap");
+                st->operators[p] = to_opercode(m, rec[j][k++].x);
+            }
+            if (k != c.n) return fail("sse_get_state: occupancy bitmap and operator count disagree");
+        }
+        st->operators_len = c.M;
+    }
+    return 0;
+}
+
 int32_t sse_get_state(sse_walkers *w, int32_t i, sse_walker_state *st) {
     if (!w || !st) return fail("null argument");
     if (i < 0 || i >= w->dw.W) return fail("sse_get_state: walker index out of range");
-    if (int32_t s = require_between_sweeps(w, "sse_get_state")) return s;
-    const sse_model *m = w->model;
-    WalkerCtl c;
-    CU(cudaMemcpyAsync(&c, w->dw.ctl + i, sizeof(c), cudaMemcpyDeviceToHost, w->stream));
-    CU(cudaStreamSynchronize(w->stream));
-    st->num_operators = c.n;
-    st->rng_draws = c.draws;
-    st->avg_worm_length = c.avg_wl;
-    st->num_worms = c.num_worms;
-    st->T = c.T;
-    if (st->operators) {
-        if (st->operators_len < c.M) { st->operators_len = c.M; return fail("sse_get_state: operators buffer too small"); }
-        std::vector<uint2> words;
-        std::vector<uint4> rec;
-        if (int32_t s = download_string(w, i, c, words, rec)) return s;
-        int64_t k = 0;
-        for (int p = 0; p < c.M; ++p) {
-            if (!((words[p >> 5].x >> (p & 31)) & 1u)) { st->operators[p] = 0; continue; }
-            if (k >= c.n) return fail("sse_get_state: corrupt occupancy bitmap");
-            st->operators[p] = to_opercode(m, rec[k++].x);
-        }
-        if (k != c.n) return fail("sse_get_state: occupancy bitmap and operator count disagree");
-    }
-    st->operators_len = c.M;
-    if (st->state) {
-        CU(cudaMemcpyAsync(st->state, w->dw.state + (size_t)i * m->dm.n_sites, m->dm.n_sites, cudaMemcpyDeviceToHost, w->stream));
-        CU(cudaStreamSynchronize(w->stream));
-    }
-    return 0;
+    return sse_get_states(w, i, 1, st);
 }
 
 int32_t sse_set_state(sse_walkers *w, int32_t i, const sse_walker_state *st) {

@@ -30,8 +30,17 @@ struct SweepStats {
     unsigned long long visits, sweeps, sum_n, sum_M, cyc_build, cyc_finish, cyc_idle, tasks;
 };
 
-// bytes of the scheduler block in shared memory: {n_done, n_need, pad x2, status[nloc_max]}
-__host__ __device__ inline int sched_bytes(int nloc_max) { return (16 + 4 * nloc_max + 15) & ~15; }
+// The scheduler block of a CTA in shared memory: {n_done, q_head, q_tail, pad, status[nloc_max], queue[nloc_max]}.
+// queue[] is a FIFO of the walkers that wait for a stream warp (entry = local index + 1, 0 = slot not written yet):
+// first come, first served, so no walker falls behind the others and a launch that gives every walker the same visit
+// budget ends for all of them at about the same time.
+__host__ __device__ inline int sched_bytes(int nloc_max) { return (16 + 8 * nloc_max + 15) & ~15; }
+
+// a worm lane (or the launch prologue) queues walker j for streaming
+__device__ __forceinline__ void stream_enqueue(uint32_t *sched, int nloc_max, int j) {
+    const uint32_t t = atomicAdd(sched + 2, 1u);
+    st_volatile_shared(sched + 4 + nloc_max + (int)(t % (uint32_t)nloc_max), (uint32_t)j + 1u);
+}
 
 // One streaming task: whatever walker w needs until it is ready for its worm lane again (or done for this launch).
 // Returns the walker's next status (WS_READY_WORM or WS_DONE).
@@ -97,8 +106,9 @@ __device__ uint32_t stream_task(const SmTab &st, const DevModel &dm, const DevWa
 
 // Role of a worm warp inside k_sweep: one lane = one walker (walkers j = lane index + m * lanes of the CTA's status table).
 template <bool INJ>
-__device__ __forceinline__ void worm_warp_role(const SmTab &st, const DevModel &dm, const DevWalkers &dw, const SweepArgs &a, uint32_t *n_done,
-                                            uint32_t *n_need, uint32_t *status, int nloc, int warp, uint32_t lane) {
+__device__ __forceinline__ void worm_warp_role(const SmTab &st, const DevModel &dm, const DevWalkers &dw, const SweepArgs &a, uint32_t *sched,
+                                            int nloc, int warp, uint32_t lane) {
+    uint32_t *n_done = sched, *status = sched + 4;
     // ------------------------------ worm warp: one lane = one walker ------------------------------
     const LaneEnv env = lane_env(st, dm, dw);
     const int nlanes = a.worm_warps * 32, me = warp * 32 + (int)lane;
@@ -159,7 +169,7 @@ __device__ __forceinline__ void worm_warp_role(const SmTab &st, const DevModel &
                 __threadfence();  // op-code stores and the control block before the hand-over
                 st_volatile_shared(status + cur, post);
                 if (post == WS_DONE) atomicAdd(n_done, 1u);
-                else atomicAdd(n_need, 1u);  // WS_NEED_STREAM: wake a stream warp
+                else stream_enqueue(sched, a.nloc_max, cur);  // WS_NEED_STREAM: join the queue of the stream warps
                 cur = -1;
             }
         }
@@ -181,38 +191,34 @@ __device__ __forceinline__ void worm_warp_role(const SmTab &st, const DevModel &
 
 // Role of a stream warp inside k_sweep: claim walkers that wait for streaming until every walker of the CTA is done.
 template <bool INJ>
-__device__ __forceinline__ void stream_warp_role(const SmTab &st, const DevModel &dm, const DevWalkers &dw, const SweepArgs &a, uint32_t *n_done,
-                                              uint32_t *n_need, uint32_t *status, int nloc, uint8_t *scratch, uint32_t lane) {
+__device__ __forceinline__ void stream_warp_role(const SmTab &st, const DevModel &dm, const DevWalkers &dw, const SweepArgs &a, uint32_t *sched,
+                                              int nloc, uint8_t *scratch, uint32_t lane) {
     // ------------------------------ stream warp: one warp = one walker ------------------------------
+    uint32_t *n_done = sched, *q_head = sched + 1, *q_tail = sched + 2, *status = sched + 4, *queue = sched + 4 + a.nloc_max;
     SweepStats ss = {0, 0, 0, 0, 0, 0, 0, 0};
     unsigned nap = 256;
     while (true) {
-        // claim a walker that waits for streaming.  An idle warp only watches two counters (one lane reads, all agree)
-        // and sleeps with exponential back-off; the status table is scanned only when somebody is waiting.
+        // take the walker that has waited longest (lane 0 pops the FIFO, all lanes agree); an idle warp only watches the
+        // queue counters and sleeps with exponential back-off
         int j = -1;
+        uint32_t done = 0;
         const long long t0 = clock64();
-        uint32_t waiting = 0, done = 0;
         if (lane == 0) {
-            waiting = ld_volatile_shared(n_need);
+            while (true) {
+                const uint32_t h = ld_volatile_shared(q_head);
+                if (h == ld_volatile_shared(q_tail)) break;
+                if (atomicCAS(q_head, h, h + 1u) != h) continue;
+                uint32_t *slot = queue + (int)(h % (uint32_t)a.nloc_max);
+                uint32_t e;
+                while ((e = ld_volatile_shared(slot)) == 0u) backoff(32);  // ticket taken, entry about to be written
+                st_volatile_shared(slot, 0u);
+                j = (int)e - 1;
+                break;
+            }
             done = ld_volatile_shared(n_done);
         }
-        waiting = __shfl_sync(FULL, waiting, 0);
+        j = __shfl_sync(FULL, j, 0);
         done = __shfl_sync(FULL, done, 0);
-        if (waiting) {
-            for (int b = 0; b < nloc && j < 0; b += 32) {
-                const int jj = b + (int)lane;
-                const bool want = jj < nloc && ld_volatile_shared(status + jj) == WS_NEED_STREAM;
-                uint32_t m = __ballot_sync(FULL, want);
-                while (m && j < 0) {  // the lowest hit is tried first
-                    const int t = __ffs(m) - 1;
-                    m &= m - 1;
-                    uint32_t got = 0;
-                    if ((int)lane == t) got = atomicCAS(status + jj, (uint32_t)WS_NEED_STREAM, (uint32_t)WS_STREAMING) == WS_NEED_STREAM;
-                    got = __shfl_sync(FULL, got, t);
-                    if (got) j = b + t;
-                }
-            }
-        }
         if (j < 0) {
             if (done >= (uint32_t)nloc) break;
             backoff(nap);
@@ -221,7 +227,7 @@ __device__ __forceinline__ void stream_warp_role(const SmTab &st, const DevModel
             continue;
         }
         nap = 256;
-        if (lane == 0) atomicSub(n_need, 1u);
+        if (lane == 0) st_volatile_shared(status + j, WS_STREAMING);
         __threadfence();  // the worm lane's writes (op codes, control block) are visible
         const int w = (int)blockIdx.x + j * (int)gridDim.x;
         const uint32_t next = stream_task<INJ>(st, dm, dw, a, w, scratch, lane, ss);
@@ -252,13 +258,13 @@ __global__ void __launch_bounds__(SWEEP_MAX_WARPS * 32, 1) k_sweep(const DevMode
     const SmTab st = stage_tables(dm, smem);
     uint32_t *sched = reinterpret_cast<uint32_t *>(smem + dm.tl.bytes);
     uint32_t *n_done = sched;          // walkers of this CTA that are WS_DONE
-    uint32_t *n_need = sched + 1;      // walkers of this CTA that are WS_NEED_STREAM
     uint32_t *status = sched + 4;
     const int warp = threadIdx.x >> 5;
     const uint32_t lane = threadIdx.x & 31;
     // walkers of this CTA: w = blockIdx.x + j * gridDim.x
     const int nloc = (dw.W - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-    if (threadIdx.x == 0) { *n_done = 0; *n_need = 0; }
+    if (threadIdx.x == 0) { sched[0] = 0; sched[1] = 0; sched[2] = 0; }
+    for (int j = threadIdx.x; j < a.nloc_max; j += blockDim.x) sched[4 + a.nloc_max + j] = 0;
     __syncthreads();
     for (int j = threadIdx.x; j < nloc; j += blockDim.x) {
         WalkerCtl *ctl = dw.ctl + ((size_t)blockIdx.x + (size_t)j * gridDim.x);
@@ -274,16 +280,16 @@ __global__ void __launch_bounds__(SWEEP_MAX_WARPS * 32, 1) k_sweep(const DevMode
         else s = ((a.reset ? a.n_sweeps : ctl->sweeps_left) > 0 && a.budget) ? WS_NEED_STREAM : WS_DONE;
         status[j] = s;
         if (s == WS_DONE) atomicAdd(n_done, 1u);
-        if (s == WS_NEED_STREAM) atomicAdd(n_need, 1u);
+        if (s == WS_NEED_STREAM) stream_enqueue(sched, a.nloc_max, j);
     }
     __syncthreads();
 
     if (warp < a.worm_warps) {
-        worm_warp_role<INJ>(st, dm, dw, a, n_done, n_need, status, nloc, warp, lane);
+        worm_warp_role<INJ>(st, dm, dw, a, sched, nloc, warp, lane);
     } else if (warp < a.worm_warps + a.stream_warps) {
         uint8_t *scratch = smem + dm.tl.bytes + sched_bytes(a.nloc_max) +
                            (size_t)(warp - a.worm_warps) * stream_scratch_bytes(dm.n_sites, a.level);
-        stream_warp_role<INJ>(st, dm, dw, a, n_done, n_need, status, nloc, scratch, lane);
+        stream_warp_role<INJ>(st, dm, dw, a, sched, nloc, scratch, lane);
     }
 }
 

@@ -112,7 +112,7 @@ class MC:
 
     def write_checkpoint(self) -> dict:
         """Carlo.write_checkpoint (sse.jl:89-107): the reference's five fields per walker (+ stream position)."""
-        return {"walkers": [self.walkers.get_state(i) for i in range(self.n_walkers)]}
+        return {"walkers": self.walkers.get_states()}
 
     def read_checkpoint(self, data: dict):
         for i, s in enumerate(data["walkers"]):

@@ -189,6 +189,24 @@ class Walkers:
                     num_worms=float(st.num_worms), operators=ops[: st.operators_len].copy(), state=state,
                     rng_draws=int(st.rng_draws), T=float(st.T))
 
+    def get_states(self, first: int = 0, count: int | None = None) -> list:
+        """Checkpoint data of `count` walkers from `first` with one round of device-to-host copies (sse_get_states)."""
+        count = self.n_walkers - first if count is None else count
+        arr = (WalkerState * count)()
+        check(self.L.sse_get_states(self.handle, first, count, arr))  # sizes
+        bufs = []
+        for j in range(count):
+            ops = np.zeros(max(int(arr[j].operators_len), 1), dtype=np.uint64)
+            state = np.zeros(self.dmodel.n_sites, dtype=np.uint8)
+            arr[j].operators = ops.ctypes.data_as(u64p)
+            arr[j].operators_len = len(ops)
+            arr[j].state = state.ctypes.data_as(u8p)
+            bufs.append((ops, state))
+        check(self.L.sse_get_states(self.handle, first, count, arr))
+        return [dict(num_operators=int(st.num_operators), avg_worm_length=float(st.avg_worm_length), num_worms=float(st.num_worms),
+                     operators=ops[: st.operators_len].copy(), state=state, rng_draws=int(st.rng_draws), T=float(st.T))
+                for st, (ops, state) in zip(arr, bufs)]
+
     def set_state(self, walker: int, s: dict):
         ops = np.ascontiguousarray(s["operators"], dtype=np.uint64)
         state = np.ascontiguousarray(s["state"], dtype=np.uint8)
