@@ -373,7 +373,45 @@ int32_t sse_model_create(const sse_model_desc *d, sse_model **out) {
             return fail("SSEData: site dimensions set by VertexData are inconsistent (bond " + std::to_string(b) + ")");
         }
         bi[b] = make_uint4((uint32_t)sa | ((uint32_t)da << 24), (uint32_t)sb | ((uint32_t)db << 24),
-                           (uint32_t)d->type_diag_off[t], (uint32_t)t);
+                           (uint32_t)d->type_diag_off[t], 0u);
+    }
+    // Estimator tables est_values[e][site][state] usually hold a handful of distinct rows (e.g. +-(1/2, -1/2) for a
+    // staggered magnetization).  With at most two estimators and at most 255 distinct rows each, the rows go to shared
+    // memory and the row index of a bond's two sites rides in the bond table, so the measurement can be fused into the
+    // diagonal-update pass without a dependent global load.
+    const int md = d->est_max_dim > 0 ? d->est_max_dim : 1;
+    std::vector<double> est_rows;
+    int est_nrows = 0;
+    bool est_compressed = d->n_estimators >= 1 && d->n_estimators <= 2;
+    if (est_compressed) {
+        std::vector<std::vector<std::vector<double>>> rows(d->n_estimators);
+        std::vector<std::vector<int>> rowid(d->n_estimators, std::vector<int>(d->n_sites, 0));
+        for (int e = 0; e < d->n_estimators && est_compressed; ++e)
+            for (int s = 0; s < d->n_sites; ++s) {
+                const double *r = d->est_values + ((size_t)e * d->n_sites + s) * md;
+                int id = -1;
+                for (size_t k = 0; k < rows[e].size(); ++k)
+                    if (memcmp(rows[e][k].data(), r, sizeof(double) * md) == 0) { id = (int)k; break; }
+                if (id < 0) {
+                    if (rows[e].size() >= 255) { est_compressed = false; break; }
+                    id = (int)rows[e].size();
+                    rows[e].emplace_back(r, r + md);
+                }
+                rowid[e][s] = id;
+            }
+        if (est_compressed) {
+            for (auto &re : rows) est_nrows = std::max(est_nrows, (int)re.size());
+            est_rows.assign((size_t)d->n_estimators * est_nrows * md, 0.0);
+            for (int e = 0; e < d->n_estimators; ++e)
+                for (size_t k = 0; k < rows[e].size(); ++k)
+                    std::copy(rows[e][k].begin(), rows[e][k].end(), est_rows.begin() + ((size_t)e * est_nrows + k) * md);
+            for (int b = 0; b < d->n_bonds; ++b) {
+                const int sa = d->bond_sites[2 * b], sb = d->bond_sites[2 * b + 1];
+                uint32_t wv = (uint32_t)rowid[0][sa] | ((uint32_t)rowid[0][sb] << 8);
+                if (d->n_estimators > 1) wv |= ((uint32_t)rowid[1][sa] << 16) | ((uint32_t)rowid[1][sb] << 24);
+                bi[b].w = wv;
+            }
+        }
     }
     // shared-memory image
     const int n_out = d->n_outcomes, n_diag = d->type_diag_off[d->n_types];
@@ -387,6 +425,8 @@ int32_t sse_model_create(const sse_model_desc *d, sse_model **out) {
     tl.off_vinfo = take(4 * nv);
     tl.off_diagv = take(2 * n_diag);
     tl.off_vneg = take(nv);
+    tl.off_estrows = est_compressed ? take(8 * (int)est_rows.size()) : -1;
+    tl.est_nrows = est_nrows;
     tl.bytes = off;
     if (tl.bytes > 64 * 1024) { return fail("sse_model_create: vertex tables exceed the 64 KB shared-memory budget"); }
     std::vector<uint8_t> blob(tl.bytes, 0);
@@ -396,6 +436,7 @@ int32_t sse_model_create(const sse_model_desc *d, sse_model **out) {
     auto *vinfo = reinterpret_cast<uint32_t *>(blob.data() + tl.off_vinfo);
     auto *diagv = reinterpret_cast<uint16_t *>(blob.data() + tl.off_diagv);
     auto *vneg = blob.data() + tl.off_vneg;
+    if (est_compressed) memcpy(blob.data() + tl.off_estrows, est_rows.data(), 8 * est_rows.size());
     for (int v = 0; v < nv; ++v) {
         const uint8_t *ls = d->leg_states + 4 * v;
         wts[v] = d->weights[v];

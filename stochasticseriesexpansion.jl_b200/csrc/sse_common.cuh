@@ -67,6 +67,8 @@ struct TabLayout {
     int off_vinfo;    // u32    [nv]  leg states packed, 8 bits per leg
     int off_diagv;    // u16    [n_diag]  global vertex id + 1, 0 = invalid
     int off_vneg;     // u8     [nv]  1 if the vertex sign is negative
+    int off_estrows;  // double [n_est][est_nrows][est_max_dim]  the distinct rows of est_values (fused measurement), or -1
+    int est_nrows;
 };
 // packed step (t1[].z / outc[].z): bits 1..13 = vertex bits of the op code (diag << 1 | gv << 2), bits 16..17 = exit leg,
 // bits 24..31 = exit worm;  .w: bits 24..31 = dim of the exit leg's site, (t1 only) bits 6..23 = offset of the 2nd outcome,
@@ -78,13 +80,15 @@ struct SmTab {
     const uint32_t *vinfo;
     const uint16_t *diagv;
     const uint8_t *vneg;
+    const double *estrows;  // nullptr if the estimator tables do not compress (see sse_model_create)
     uint32_t t1_s, outc_s;  // shared-space addresses of t1 / outc
 };
 
 struct DevModel {
     int n_sites, n_bonds, nv, max_worm, n_est, est_max_dim, norm_sites;
     double energy_offset;
-    const uint4 *bond_info;   // [n_bonds] {site_a | dim_a << 24, site_b | dim_b << 24, diag table base, type}
+    const uint4 *bond_info;   // [n_bonds] {site_a | dim_a << 24, site_b | dim_b << 24, diag table base,
+                              //            row of est_values of (estimator 0, site a) | (0, b) << 8 | (1, a) << 16 | (1, b) << 24}
     const uint8_t *site_dim;  // [n_sites]
     const double *est_values; // [n_est][n_sites][est_max_dim]
     const uint8_t *tab_blob;  // TabLayout image
@@ -286,6 +290,7 @@ __device__ __forceinline__ SmTab stage_tables(const DevModel &dm, uint8_t *smem)
     st.vinfo = reinterpret_cast<const uint32_t *>(smem + dm.tl.off_vinfo);
     st.diagv = reinterpret_cast<const uint16_t *>(smem + dm.tl.off_diagv);
     st.vneg = reinterpret_cast<const uint8_t *>(smem + dm.tl.off_vneg);
+    st.estrows = dm.tl.off_estrows >= 0 ? reinterpret_cast<const double *>(smem + dm.tl.off_estrows) : nullptr;
     st.t1_s = (uint32_t)__cvta_generic_to_shared(st.t1);
     st.outc_s = (uint32_t)__cvta_generic_to_shared(st.outc);
     return st;

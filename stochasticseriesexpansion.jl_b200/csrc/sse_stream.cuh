@@ -317,10 +317,42 @@ __device__ __forceinline__ ChunkIn diag_stage_b(const DevModel &dm, const Ctx &c
     return in;
 }
 
-template <bool INJ>
-__device__ void phase_diag_build(const SmTab &st, const DevModel &dm, const DevWalkers &dw, Ctx &c, bool do_diag) {
+// MEAS: Carlo.measure! of the sweep that just ended (src/sse.jl:70-87, measure_opstring! :321-376) is evaluated on the way:
+// this pass reads, in slot order and with the state propagated along the string, exactly the configuration measure! would
+// see, so the separate pass over the string is saved.  Needs the compressed estimator rows
+// (st.estrows, at most two estimators); the observables go to meas_out[n_obs].
+struct MeasAcc {  // per-lane partial sums of one estimator (magnetization_estimator.jl:152-158)
+    double tmpmag, mag, absmag, mag2, mag4;
+};
+
+template <bool INJ, bool MEAS = false>
+__device__ void phase_diag_build(const SmTab &st, const DevModel &dm, const DevWalkers &dw, Ctx &c, bool do_diag,
+                                 double *meas_out = nullptr) {
     const uint32_t lane = c.lane, lt = lanemask_lt();
     const int N = dm.n_sites;
+    // ---- measurement, part 1: everything that refers to the configuration BEFORE this diagonal update ----
+    const double meas_nops = (double)c.n;
+    const int md = dm.est_max_dim;
+    MeasAcc ma[2];
+    uint32_t neg = 0;
+    if (MEAS) {
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+            ma[g].tmpmag = ma[g].mag = ma[g].absmag = ma[g].mag2 = ma[g].mag4 = 0.0;
+            if (g < dm.n_est) {  // init (magnetization_estimator.jl:96-123)
+                const double *ev = dm.est_values + (size_t)g * N * md;
+                double part = 0.0;
+                for (int s = lane; s < N; s += 32) part += __ldg(ev + (size_t)s * md + (c.state[s] - 1));
+                ma[g].tmpmag = warp_sum_f64(part);
+                if (lane == 0) {
+                    ma[g].mag = ma[g].tmpmag;
+                    ma[g].absmag = fabs(ma[g].tmpmag);
+                    ma[g].mag2 = ma[g].tmpmag * ma[g].tmpmag;
+                    ma[g].mag4 = ma[g].mag2 * ma[g].mag2;
+                }
+            }
+        }
+    }
     if (do_diag && 2ll * (long long)c.n >= (long long)c.M) {  // n >= 0.5*M  (sse.jl:138)
         long long newM = (3ll * (long long)c.M) / 2 + 100;     // floor(1.5*M + 100) (sse.jl:143)
         if (newM > dw.M_cap) { c.flags |= SSE_FLAG_M_OVERFLOW; return; }
@@ -382,6 +414,37 @@ __device__ void phase_diag_build(const SmTab &st, const DevModel &dm, const DevW
         const uint4 bi = lds128(c.biring_s + 16u * (32u * (uint32_t)(ch & 1) + lane));
         const uint32_t sa = bi.x & NONE24, sb = bi.y & NONE24;
         uint32_t newop = op;
+
+        if (MEAS) {  // ---- measurement, part 2: this chunk's (old) operators ----
+            neg += __popc(__ballot_sync(FULL, nonid && st.vneg[gv]));  // measure_sign (sse.jl:305-314)
+            const uint32_t moffm = __ballot_sync(FULL, is_off);
+            const uint32_t mvi = is_off ? st.vinfo[gv] : 0u;
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+                if (g >= dm.n_est) break;
+                double scan = 0.0;
+                if (is_off) {  // off-diagonal: tmpmag += sum_l sign*(m(top_l) - m(bottom_l)) (:134-150)
+                    const double *ea = st.estrows + ((size_t)g * dm.tl.est_nrows + ((bi.w >> (16 * g)) & 0xffu)) * md;
+                    const double *eb = st.estrows + ((size_t)g * dm.tl.est_nrows + ((bi.w >> (16 * g + 8)) & 0xffu)) * md;
+                    scan = (ea[((mvi >> 16) & 0xffu) - 1] - ea[(mvi & 0xffu) - 1]) + (eb[(mvi >> 24) - 1] - eb[((mvi >> 8) & 0xffu) - 1]);
+                }
+                if (moffm) {  // inclusive prefix sum over the chunk, in slot order
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const double up = shfl_up_f64(scan, d);
+                        if ((int)lane >= d) scan += up;
+                    }
+                }
+                if (nonid) {  // every non-identity operator is one sample (:152-158)
+                    const double v = ma[g].tmpmag + scan, v2 = v * v;
+                    ma[g].mag += v;
+                    ma[g].absmag += fabs(v);
+                    ma[g].mag2 += v2;
+                    ma[g].mag4 += v2 * v2;
+                }
+                if (moffm) ma[g].tmpmag += shfl_f64(scan, 31);
+            }
+        }
 
         if (do_diag) {
             // State seen by each identity slot = state at chunk start overridden by earlier off-diagonal
@@ -510,6 +573,37 @@ __device__ void phase_diag_build(const SmTab &st, const DevModel &dm, const DevW
         }
     }
     __syncwarp();
+    if (MEAS) {  // ---- measurement, part 3: the observables (sse.jl:73-82; result, magnetization_estimator.jl:205-230) ----
+        const double sign = (neg & 1u) ? -1.0 : 1.0;  // sse.jl:313
+        if (lane == 0) {
+            meas_out[SSE_OBS_SIGN] = sign;
+            meas_out[SSE_OBS_OPERATOR_COUNT] = meas_nops;
+            meas_out[SSE_OBS_SIGN_OPERATOR_COUNT] = sign * meas_nops;
+            meas_out[SSE_OBS_SIGN_OPERATOR_COUNT2] = sign * (meas_nops * meas_nops);
+            meas_out[SSE_OBS_SIGN_ENERGY] = -sign * (meas_nops * c.T + dm.energy_offset) / (double)dm.norm_sites;
+            meas_out[SSE_OBS_WORM_LENGTH_FRACTION] = c.last_wlf;
+        }
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+            if (g >= dm.n_est) break;
+            double m1 = warp_sum_f64(ma[g].mag), mabs = warp_sum_f64(ma[g].absmag), m2 = warp_sum_f64(ma[g].mag2), m4 = warp_sum_f64(ma[g].mag4);
+            if (lane == 0) {
+                const double ns = 1.0 + meas_nops;
+                const double norm = 1.0 / (double)dm.norm_sites;
+                m1 *= norm;
+                mabs *= norm;
+                m2 *= norm * norm;
+                m4 *= (norm * norm) * (norm * norm);
+                double *o = meas_out + SSE_OBS_FIXED + SSE_OBS_PER_ESTIMATOR * g;
+                o[0] = sign * m1 / ns;
+                o[1] = sign * mabs / ns;
+                o[2] = sign * m2 / ns;
+                o[3] = sign * m4 / ns;
+                o[4] = sign * (1.0 / c.T / (ns + 1.0) / ns * (m1 * m1 + m2) * (double)dm.norm_sites);
+            }
+        }
+        __syncwarp();
+    }
     c.n = n;
     c.G = Gn;
     c.draws = draws;

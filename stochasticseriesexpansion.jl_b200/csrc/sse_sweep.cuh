@@ -56,14 +56,18 @@ __device__ uint32_t stream_task(const SmTab &st, const DevModel &dm, const DevWa
     uint32_t worms_left = 0, next = WS_DONE;
     __syncwarp();
     while (true) {
+        bool fuse_measure = false;  // Carlo.measure! of the sweep that ends here rides on the next sweep's diagonal update
         if (phase == 1) {  // the worms of the sweep in flight are done: rest of worm_update, then Carlo.measure!
             const long long t0 = clock64();
             worm_finish<INJ>(st, dm, dw, c, a.thermalized != 0, w, 1.0 + (double)sweep_visits);  // sse.jl:194
             if (!(c.flags & FATAL_FLAGS)) {
                 if (a.measure) {
-                    double *out = dw.obs_out + (size_t)w * dw.n_obs;
-                    phase_measure(st, dm, dw, c, out);
-                    accumulate_obs(dw, w, lane, out);
+                    fuse_measure = st.estrows != nullptr && sweeps_left > 1 && budget_left != 0;  // a build follows below
+                    if (!fuse_measure) {
+                        double *out = dw.obs_out + (size_t)w * dw.n_obs;
+                        phase_measure(st, dm, dw, c, out);
+                        accumulate_obs(dw, w, lane, out);
+                    }
                 }
                 ++ss.sweeps;
                 ss.sum_n += (unsigned long long)c.n;
@@ -76,7 +80,13 @@ __device__ uint32_t stream_task(const SmTab &st, const DevModel &dm, const DevWa
         }
         if ((c.flags & FATAL_FLAGS) || sweeps_left <= 0 || budget_left == 0) break;
         const long long t0 = clock64();
-        phase_diag_build<INJ>(st, dm, dw, c, true);  // sse.jl:63-64
+        if (fuse_measure) {
+            double *out = dw.obs_out + (size_t)w * dw.n_obs;
+            phase_diag_build<INJ, true>(st, dm, dw, c, true, out);  // sse.jl:63-64 + the measurement of the sweep before
+            if (!(c.flags & FATAL_FLAGS)) accumulate_obs(dw, w, lane, out);
+        } else {
+            phase_diag_build<INJ>(st, dm, dw, c, true);  // sse.jl:63-64
+        }
         ss.cyc_build += (unsigned long long)(clock64() - t0);
         if (c.flags & FATAL_FLAGS) break;
         phase = 1;

@@ -236,8 +236,8 @@ def test_gpu_full_size_parity_config4():
 
     L, beta = 48, 48
     model = dimer_bilayer(L)
-    # <n> ~ beta * sum_b <W_b>: measured on the oracle at small L, ~1.45 operators per bond and unit of beta
-    _body_full_size_parity(L, beta, 5, model=model, n_est=1.6 * beta * 2 * L * L, per_level=3, walkers=2)
+    # measured on the oracle at L = 6 and 8: n ~ 2.7 operators and M ~ 7.6 slots per bond and unit of beta
+    _body_full_size_parity(L, beta, 5, model=model, n_est=2.9 * beta * 2 * L * L, per_level=3, walkers=2)
 
 
 def _body_bani_cold_task(L, T, walkers, sweeps, budget):
