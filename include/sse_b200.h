@@ -130,6 +130,14 @@ int32_t sse_n_observables(const sse_walkers *w);
 int64_t sse_walker_bytes(const sse_model *m, int64_t m_capacity, int64_t n_capacity);
 int64_t sse_device_bytes(const sse_walkers *w);
 
+/* The reference resizes its operator string in place (src/sse.jl:138-145); the device arrays have fixed capacities.
+ * sse_grow_capacity moves every walker to larger ones (old and new arrays coexist during the move) and clears a pending
+ * "string outgrew m_capacity" condition: that overflow is detected before the sweep modifies anything, so the walker
+ * simply continues with its next sse_sweep.  Running out of n_capacity in the middle of a diagonal update is NOT
+ * recoverable (the record ring is partly rewritten): grow n_capacity while sse_get_num_operators is still below it.
+ * Needs walkers between sweeps. */
+int32_t sse_grow_capacity(sse_walkers *w, int64_t m_capacity, int64_t n_capacity);
+
 /* Carlo.init!(mc, ctx, params) (src/sse.jl:47-60): random state, `init_opstring_cutoff` identities
  * (< 0: round(n_sites*T) per walker), `diagonal_warmup_sweeps` diagonal updates. Synchronous. */
 int32_t sse_init(sse_walkers *w, int64_t init_opstring_cutoff, int32_t diagonal_warmup_sweeps);
@@ -153,6 +161,9 @@ int32_t sse_sync(sse_walkers *w);
 int32_t sse_advance(sse_walkers *w, int32_t max_sweeps, uint64_t visit_budget, int32_t thermalized, int32_t measure);
 /* Complete the sweeps that sse_advance left in flight (no new sweep is started).  Asynchronous. */
 int32_t sse_finish_sweeps(sse_walkers *w, int32_t thermalized, int32_t measure);
+/* Resume an sse_sweep that ended with an error some walkers can recover from (sse_grow_capacity after "string outgrew
+ * m_capacity"): every walker does the sweeps of that call it has not done yet, so the batch is in step again.  Asynchronous. */
+int32_t sse_continue_sweeps(sse_walkers *w, int32_t thermalized, int32_t measure);
 /* sweeps_done[n_walkers]: completed sweeps since sse_init / sse_set_state; in_flight[n_walkers] (may be NULL): 1 if
  * the walker is parked inside a sweep. */
 int32_t sse_get_progress(sse_walkers *w, uint64_t *sweeps_done, uint8_t *in_flight);

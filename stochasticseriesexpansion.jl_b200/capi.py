@@ -135,6 +135,7 @@ def lib():
         "sse_walkers_create": (C.c_int32, [vp, C.POINTER(WalkersOpts), C.POINTER(vp)]),
         "sse_walkers_destroy": (C.c_int32, [vp]),
         "sse_set_stream": (C.c_int32, [vp, vp]),
+        "sse_grow_capacity": (C.c_int32, [vp, C.c_int64, C.c_int64]),
         "sse_n_observables": (C.c_int32, [vp]),
         "sse_device_bytes": (C.c_int64, [vp]),
         "sse_walker_bytes": (C.c_int64, [vp, C.c_int64, C.c_int64]),
@@ -165,6 +166,7 @@ def lib():
         "sse_set_launch_shape": (C.c_int32, [vp, C.c_int32, C.c_int32]),
         "sse_advance": (C.c_int32, [vp, C.c_int32, C.c_uint64, C.c_int32, C.c_int32]),
         "sse_finish_sweeps": (C.c_int32, [vp, C.c_int32, C.c_int32]),
+        "sse_continue_sweeps": (C.c_int32, [vp, C.c_int32, C.c_int32]),
         "sse_get_progress": (C.c_int32, [vp, u64p, u8p]),
         "sse_set_injected_stream": (C.c_int32, [vp, u64p, C.c_int64]),
         "sse_dbg_diagonal_update": (C.c_int32, [vp]),
@@ -184,12 +186,12 @@ def lib():
 
 EXPORTED_SYMBOLS = [
     "sse_last_error", "sse_abi_version", "sse_model_create", "sse_model_destroy", "sse_walkers_create",
-    "sse_walkers_destroy", "sse_set_stream", "sse_n_observables", "sse_device_bytes", "sse_walker_bytes", "sse_init", "sse_sweep",
+    "sse_walkers_destroy", "sse_set_stream", "sse_grow_capacity", "sse_n_observables", "sse_device_bytes", "sse_walker_bytes", "sse_init", "sse_sweep",
     "sse_sync", "sse_measure", "sse_fetch_accumulators", "sse_accumulators_device_ptr", "sse_fetch_counters",
     "sse_comm_unique_id", "sse_comm_init", "sse_reduce_bins",
     "sse_get_state", "sse_get_states", "sse_set_state", "sse_get_flags", "sse_pt_log_weight_ratio", "sse_set_temperature",
     "sse_get_num_operators", "sse_get_temperatures", "sse_pt_set_ladder", "sse_pt_get_ladder", "sse_pt_exchange", "sse_pt_uniforms", "sse_double_beta", "sse_set_controller", "sse_set_launch_shape",
-    "sse_advance", "sse_finish_sweeps", "sse_get_progress",
+    "sse_advance", "sse_finish_sweeps", "sse_continue_sweeps", "sse_get_progress",
     "sse_set_injected_stream", "sse_dbg_diagonal_update", "sse_dbg_make_vertex_list",
     "sse_dbg_worm_update", "sse_dbg_worm_traverse", "sse_dbg_get_vertex_list",
 ]

@@ -321,6 +321,30 @@ __global__ void k_pt_exchange(const DevWalkers dw, int32_t *ladder, int n_ladder
     }
 }
 
+// sse_grow_capacity: every walker's bitmap words and records (unrolled from its ring, generation start back at 0) move to
+// arrays of the new capacities; a pending "string outgrew m_capacity" flag is cleared, because that overflow is detected
+// before the sweep modifies anything.  One warp per walker.
+__global__ void k_grow(const DevWalkers src, uint2 *new_words, long long new_Mw_cap, uint4 *new_rec, long long new_R_cap) {
+    const int w = blockIdx.x * PHASE_WARPS + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (w >= src.W) return;
+    WalkerCtl *ctl = src.ctl + w;
+    const int M = ctl->M, n = ctl->n;
+    const uint32_t G = ctl->G;
+    const uint2 *ow = src.words + (size_t)w * src.Mw_cap;
+    uint2 *nw = new_words + (size_t)w * new_Mw_cap;
+    const int used = (M + 31) / 32;
+    for (long long i = lane; i < new_Mw_cap; i += 32) nw[i] = i < used ? ow[i] : make_uint2(0u, 0u);
+    const uint4 *orec = src.rec + (size_t)w * src.R_cap;
+    uint4 *nrec = new_rec + (size_t)w * new_R_cap;
+    for (int k = lane; k < n; k += 32) nrec[k] = orec[ring(G, (uint32_t)src.R_cap, (uint32_t)k)];
+    __syncwarp();
+    if (lane == 0) {
+        ctl->G = 0;
+        ctl->flags &= ~SSE_FLAG_M_OVERFLOW;
+    }
+}
+
 int64_t ring_size(int64_t n_cap) { return n_cap + std::max<int64_t>(2048, n_cap / 16); }
 
 }  // namespace
@@ -582,6 +606,53 @@ int32_t sse_walkers_create(const sse_model *m, const sse_walkers_opts *o, sse_wa
     return 0;
 }
 
+int32_t sse_grow_capacity(sse_walkers *w, int64_t m_capacity, int64_t n_capacity) {
+    if (!w) return fail("null handle");
+    DevWalkers &dw = w->dw;
+    if (((m_capacity + 31) & ~31ll) < dw.M_cap || n_capacity < dw.n_cap) return fail("sse_grow_capacity: capacities can only grow");
+    if (m_capacity >= (1ll << 31) || n_capacity > (1ll << 22) - 1) return fail("sse_grow_capacity: capacity out of range (m < 2^31, n <= 2^22 - 1)");
+    CU(cudaSetDevice(w->model->device));
+    CU(cudaStreamSynchronize(w->stream));
+    {  // walkers parked inside a sweep keep links into their ring: finish those sweeps first
+        std::vector<uint32_t> ph;
+        if (int32_t s = get_field(w, CTL_OFF(phase), ph)) return s;
+        for (int i = 0; i < dw.W; ++i)
+            if (ph[i]) return fail("sse_grow_capacity: walker " + std::to_string(i) + " is parked inside a sweep; call sse_finish_sweeps first");
+    }
+    const int64_t M_cap = (m_capacity + 31) & ~31ll, Mw_cap = M_cap / 32, R_cap = ring_size(n_capacity);
+    uint2 *nwords = nullptr;
+    uint4 *nrec = nullptr;
+    CU(cudaMalloc((void **)&nwords, sizeof(uint2) * (size_t)dw.W * Mw_cap));
+    if (cudaMalloc((void **)&nrec, sizeof(uint4) * (size_t)dw.W * R_cap) != cudaSuccess) {
+        cudaFree(nwords);
+        return fail("sse_grow_capacity: out of device memory (old and new arrays must coexist during the move)");
+    }
+    const int grid = (dw.W + PHASE_WARPS - 1) / PHASE_WARPS;
+    SSE_LAUNCH_KERNEL(k_grow, grid, PHASE_WARPS * 32, 0, w->stream, dw, nwords, (long long)Mw_cap, nrec, (long long)R_cap);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(w->stream));
+    for (void *&p : w->allocs) {
+        if (p == dw.words) { cudaFree(p); p = nwords; }
+        else if (p == dw.rec) { cudaFree(p); p = nrec; }
+    }
+    w->bytes += (int64_t)(sizeof(uint2) * (size_t)dw.W * (Mw_cap - dw.Mw_cap) + sizeof(uint4) * (size_t)dw.W * (R_cap - dw.R_cap));
+    dw.words = nwords;
+    dw.rec = nrec;
+    dw.M_cap = M_cap;
+    dw.Mw_cap = Mw_cap;
+    dw.n_cap = n_capacity;
+    dw.R_cap = R_cap;
+    w->have_vl = false;
+    // the fatal marker is rebuilt from the remaining flags
+    std::vector<uint32_t> f;
+    if (int32_t s = get_field(w, CTL_OFF(flags), f)) return s;
+    unsigned long long any = 0;
+    for (uint32_t x : f) any |= (x & FATAL_FLAGS) ? 1ull : 0ull;
+    CU(cudaMemcpyAsync(dw.counters + SSE_CNT_ANY_FATAL, &any, sizeof(any), cudaMemcpyHostToDevice, w->stream));
+    CU(cudaStreamSynchronize(w->stream));
+    return 0;
+}
+
 int32_t sse_set_launch_shape(sse_walkers *w, int32_t worm_warps, int32_t stream_warps) {
     if (!w) return fail("null handle");
     if (worm_warps < 0 || stream_warps < 0) return fail("sse_set_launch_shape: negative warp count");
@@ -689,6 +760,12 @@ int32_t sse_finish_sweeps(sse_walkers *w, int32_t thermalized, int32_t measure) 
     if (int32_t s = launch_sweep(w, 0, ~0ull, 1, thermalized, measure)) return s;
     w->maybe_in_flight = false;
     return 0;
+}
+
+int32_t sse_continue_sweeps(sse_walkers *w, int32_t thermalized, int32_t measure) {
+    if (!w) return fail("null handle");
+    // reset = 0: every walker keeps the quota the interrupted sse_sweep left it with
+    return launch_sweep(w, 0, ~0ull, 0, thermalized, measure);
 }
 
 int32_t sse_get_progress(sse_walkers *w, uint64_t *sweeps_done, uint8_t *in_flight) {

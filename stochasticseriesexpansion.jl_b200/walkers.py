@@ -76,6 +76,7 @@ class Walkers:
         o.num_worms_attenuation_factor = num_worms_attenuation_factor
         o.init_num_worms = init_num_worms
         self.m_capacity = o.m_capacity
+        self.n_capacity = o.n_capacity
         self.target_worm_length_fraction = float(target_worm_length_fraction)
         self.num_worms_attenuation_factor = float(num_worms_attenuation_factor)
         self.handle = C.c_void_p()
@@ -97,16 +98,39 @@ class Walkers:
     def set_stream(self, cuda_stream: int):
         check(self.L.sse_set_stream(self.handle, C.c_void_p(cuda_stream)))
 
+    def grow_capacity(self, m_capacity: int, n_capacity: int):
+        """Move every walker to larger arrays (sse_grow_capacity); a pending m_capacity overflow is cleared."""
+        check(self.L.sse_grow_capacity(self.handle, int(m_capacity), int(n_capacity)))
+        self.m_capacity = int(m_capacity)
+        self.n_capacity = int(n_capacity)
+
     def device_bytes(self) -> int:
         return int(self.L.sse_device_bytes(self.handle))
 
     def init(self, init_opstring_cutoff: int = -1, diagonal_warmup_sweeps: int = 5):
         check(self.L.sse_init(self.handle, init_opstring_cutoff, diagonal_warmup_sweeps))
 
-    def sweep(self, n_sweeps: int = 1, thermalized: bool = False, measure: bool = False, sync: bool = True):
+    def sweep(self, n_sweeps: int = 1, thermalized: bool = False, measure: bool = False, sync: bool = True, auto_grow: bool = False):
+        """Carlo.sweep! x n_sweeps for every walker.  auto_grow (needs sync): when a string outgrows m_capacity — the
+        reference would resize it (sse.jl:138-145) — the arrays are doubled with sse_grow_capacity and the call is resumed
+        (sse_continue_sweeps), and n_capacity grows ahead of the operator count; the trajectories are unchanged."""
         check(self.L.sse_sweep(self.handle, n_sweeps, int(thermalized), int(measure)))
-        if sync:
+        if not sync:
+            return
+        if not auto_grow:
             self.sync()
+            return
+        while True:
+            try:
+                self.sync()
+                break
+            except capi.SSEError as e:
+                if "m_capacity" not in str(e):
+                    raise
+                self.grow_capacity(2 * self.m_capacity, self.n_capacity)
+                check(self.L.sse_continue_sweeps(self.handle, int(thermalized), int(measure)))
+        if self.num_operators().max() > 0.8 * self.n_capacity:
+            self.grow_capacity(self.m_capacity, min((1 << 22) - 1, int(1.5 * self.n_capacity)))
 
     def advance(self, visit_budget: int, max_sweeps: int = 2**31 - 1, thermalized: bool = False, measure: bool = False,
                 sync: bool = True):

@@ -291,3 +291,55 @@ def test_emu_device_replica_exchange(emu):
 @pytest.mark.gpu
 def test_gpu_device_replica_exchange():
     _body_device_replica_exchange()
+
+
+def _body_grow_capacity():
+    """The reference resizes its string in place (sse.jl:138-145); here the capacity is fixed, the overflow is loud, and
+    sse_grow_capacity lets the same walkers continue on exactly the oracle's trajectory."""
+    from helpers import heisenberg_square
+
+    model = heisenberg_square(4, False)
+    dm, om = G._pair(model)
+    Ts = np.array([0.08, 0.5, 0.12])
+    gw = Walkers(dm, Ts, m_capacity=600, n_capacity=400, seed=61)
+    gw.init()
+    done = 0
+    with pytest.raises(SSEError, match="m_capacity"):
+        for _ in range(60):
+            gw.sweep(1)
+            done += 1
+    sd, _ = gw.progress()  # walkers that hit the limit stopped BEFORE their next sweep; the others went on
+    with pytest.raises(SSEError):
+        gw.grow_capacity(100, 400)
+    gw.grow_capacity(4096, 1024)
+    # every walker continues; compare each at its own count
+    gw.sweep(25)
+    sd2, fl = gw.progress()
+    assert not fl.any() and (sd2 >= sd + 24).all()
+    for i in range(len(Ts)):
+        ow = OracleWalker(om, float(Ts[i]), seed=61, walker_id=i)
+        ow.init()
+        ow.sweep(int(sd2[i]))
+        G._same_state(gw.get_state(i), ow.get_state(), f"walker {i} after growing, {sd2[i]} sweeps")
+    assert gw.get_state(0)["operators"].shape[0] > 600
+    # the same through sweep(auto_grow=True): the call is resumed, the batch stays in step
+    gw = Walkers(dm, Ts, m_capacity=600, n_capacity=300, seed=61)
+    gw.init()
+    for _ in range(12):
+        gw.sweep(5, auto_grow=True)
+    sd3, fl = gw.progress()
+    assert (sd3 == 60).all() and not fl.any() and gw.m_capacity > 600 and gw.n_capacity > 300
+    for i in range(len(Ts)):
+        ow = OracleWalker(om, float(Ts[i]), seed=61, walker_id=i)
+        ow.init()
+        ow.sweep(60)
+        G._same_state(gw.get_state(i), ow.get_state(), f"auto_grow walker {i}")
+
+
+def test_emu_grow_capacity(emu):
+    _body_grow_capacity()
+
+
+@pytest.mark.gpu
+def test_gpu_grow_capacity():
+    _body_grow_capacity()
