@@ -169,14 +169,15 @@ int32_t sweep_shape(const sse_walkers *w, SweepShape &sh) {
     if (ww < 1 || sw < 1 || ww + sw > SWEEP_MAX_WARPS) return fail("launch shape: need 1 <= worm_warps, 1 <= stream_warps, worm_warps + stream_warps <= 16");
     const int budget = 227 * 1024 - 1024;
     const int fixed = m->dm.tl.bytes + sched_bytes(sh.nloc_max);
-    // stream warps keep state[] and mark[] (level 1) and vlast[] (level 2) of their walker in shared memory: level 2 if at
-    // least 8 warps (or all that were asked for) fit, else level 1 if at least 4 fit, else everything stays in global memory
+    // stream warps keep state[] and mark[] (level 1) and vlast[] (level 2) of their walker in shared memory.  The number
+    // of stream warps matters more than the level (measured at L = 64: 10 warps at level 1 beat 9 at level 2 by 5 %): the
+    // highest level at which all wanted warps fit wins; otherwise level 1 with what fits (at least 4), else global memory.
     int max_level = 2;
     if (const char *lv = getenv("SSE_B200_SMEM_LEVEL")) max_level = std::min(max_level, std::max(0, atoi(lv)));
     sh.level = 0;
     for (int level = max_level; level >= 1; --level) {
         const int fit = (budget - fixed) / stream_scratch_bytes(N, level);
-        if (fit >= std::min(sw, level == 2 ? 8 : 4)) {
+        if (fit >= sw || (level == 1 && fit >= 4)) {
             sh.level = level;
             sw = std::min(sw, fit);
             break;
@@ -927,12 +928,14 @@ int32_t sse_get_states(sse_walkers *w, int32_t first, int32_t count, sse_walker_
     if (!w || !sts) return fail("null argument");
     if (first < 0 || count < 0 || first + count > w->dw.W) return fail("sse_get_states: walker range out of bounds");
     if (count == 0) return 0;
-    if (int32_t s = require_between_sweeps(w, "sse_get_state")) return s;
     const sse_model *m = w->model;
     const int N = m->dm.n_sites;
     std::vector<WalkerCtl> ctl(count);
     CU(cudaMemcpyAsync(ctl.data(), w->dw.ctl + first, sizeof(WalkerCtl) * count, cudaMemcpyDeviceToHost, w->stream));
     CU(cudaStreamSynchronize(w->stream));
+    for (int j = 0; j < count; ++j)  // only the walkers asked for must be between two sweeps
+        if (ctl[j].phase)
+            return fail("sse_get_state: walker " + std::to_string(first + j) + " is parked inside a sweep (sse_advance); call sse_finish_sweeps first");
     std::vector<std::vector<uint2>> words(count);
     std::vector<std::vector<uint4>> rec(count);
     for (int j = 0; j < count; ++j) {

@@ -114,7 +114,7 @@ def _body_advance_parks_anywhere(name, budgets):
     done, in_flight = gw.progress()
     assert in_flight.any()  # with these budgets somebody is parked inside a sweep
     with pytest.raises(SSEError):
-        gw.get_state(0)     # ... and says so instead of returning a half-updated configuration
+        gw.get_state(int(np.nonzero(in_flight)[0][0]))  # ... and says so instead of returning a half-updated configuration
     gw.finish_sweeps(thermalized=False)
     done2, in_flight2 = gw.progress()
     assert not in_flight2.any()
