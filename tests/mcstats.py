@@ -37,16 +37,23 @@ def run_oracle_task(om, model, T, sweeps, therm, binsize, seed=1, walker_id=0):
     return evaluate(model, {k: np.array(v) for k, v in bins.items() if len(v)})
 
 
-def run_gpu_tasks(dm, model, Ts, sweeps, therm, binsize, seed=1, m_capacity=None, replicas=1):
-    """All temperatures at once: walker i*replicas+r runs T[i]; bins of the replicas are pooled."""
+def run_gpu_tasks(dm, model, Ts, sweeps, therm, binsize, seed=1, m_capacity=None, replicas=1, doublings=0):
+    """All temperatures at once: walker i*replicas+r runs T[i]; bins of the replicas are pooled.
+    doublings > 0: the walkers start 2**doublings times hotter and are grown by beta doubling before the `therm` sweeps at
+    their temperature (no cold-start transient with its 1e8-visit worms, so no seed needs screening)."""
     from sse_b200.mc import default_capacity
     from sse_b200.walkers import Walkers
 
     Ts = np.asarray(Ts, dtype=np.float64)
     Tw = np.repeat(Ts, replicas)
     m_def, n_def = default_capacity(dm.sse_data, float(Ts.min()))
+    if doublings > 0:
+        m_def *= 2  # a doubled string is twice as long as the hotter walker's (slots cost 0.25 B)
     gw = Walkers(dm, Tw, m_capacity=m_capacity or m_def, n_capacity=n_def if not m_capacity else None, seed=seed)
-    gw.init()
+    if doublings > 0:
+        gw.thermalize_by_beta_doubling(doublings, sweeps_per_level=max(10, therm // 10))
+    else:
+        gw.init()
     done = 0
     while done < therm:
         k = min(500, therm - done)
