@@ -33,14 +33,14 @@ def main():
         dm = DeviceModel(model=model, desc=desc, keep=keep, sse_data=sd)
         om = OracleModel(desc=desc, keep=keep, sse_data=sd)
         for r in range(rounds):
-            for chains in (1, 2, 4):
+            for chains in ((1, 1), (2, 3), (1, 8)):  # launch shapes (worm warps, stream warps)
                 W = int(rng.integers(3, 14))
                 Ts = rng.uniform(0.15, 2.5, size=W)  # below ~0.1 the S=1 model launches 1e8-visit worms early on
                 seed = int(rng.integers(1, 2**40))
                 off = int(rng.integers(0, 1000))
                 n_th, n_ms = int(rng.integers(5, 40)), int(rng.integers(1, 12))
                 gw = Walkers(dm, Ts, m_capacity=16384, seed=seed, walker_id_offset=off)
-                gw.set_walkers_per_warp(chains)
+                gw.set_launch_shape(*chains)
                 gw.init()
                 gw.sweep(n_th, thermalized=False)
                 gw.sweep(n_ms, thermalized=True, measure=True)
@@ -57,10 +57,10 @@ def main():
                     osums, ocounts = ow.fetch_accumulators()
                     ok = ok and np.array_equal(counts[i], ocounts) and np.allclose(sums[i], osums, rtol=1e-12, atol=1e-300)
                     if not ok:
-                        print(f"MISMATCH {name} chains={chains} seed={seed} walker={i} T={Ts[i]}")
+                        print(f"MISMATCH {name} shape={chains} seed={seed} walker={i} T={Ts[i]}")
                         sys.exit(1)
                 cases += W
-                print(f"ok {name:16s} chains={chains} walkers={W:2d} sweeps={n_th}+{n_ms} seed={seed}", flush=True)
+                print(f"ok {name:16s} shape={chains} walkers={W:2d} sweeps={n_th}+{n_ms} seed={seed}", flush=True)
     print(f"soak ok: {cases} walker runs bit-identical to the oracle in {time.time() - t0:.0f} s")
 
 

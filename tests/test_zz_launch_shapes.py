@@ -343,3 +343,23 @@ def test_emu_grow_capacity(emu):
 @pytest.mark.gpu
 def test_gpu_grow_capacity():
     _body_grow_capacity()
+
+
+@pytest.mark.gpu
+def test_gpu_temperature_sweep_tool():
+    """profiles/tools/temperature_sweep.py (BASELINE configs[4] at small L, one rank): bins reduced per temperature inside
+    the library, device-side replica exchange between bins, energies within 4 sigma of the CPU oracle's."""
+    import argparse
+    import os
+    import sys
+
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "profiles", "tools"))
+    import temperature_sweep as ts
+
+    args = argparse.Namespace(L=4, beta_max=6.0, T_max=2.0, n_T=4, replicas=24, doublings=2, per_level=10, therm=40, bins=12,
+                              binsize=25, exchange=True, oracle_check=True, oracle_points=4, oracle_bins=20, oracle_binsize=100,
+                              seed=99)
+    line = ts.run(args)
+    assert line["oracle"]["max_abs_z"] < 4.0, line["oracle"]
+    assert 0.0 < line["pt_accept"] <= 1.0
+    assert np.all(np.diff(line["operator_count"]) < 0)  # colder temperatures carry longer strings
