@@ -21,8 +21,14 @@
 using namespace sse;
 
 // Kernel launches go through one macro so that the test-only warp emulator (tests/emu) can compile this file with g++.
+// A launch first discards whatever error another library left in the runtime's per-thread slot (NCCL's device probing
+// leaves cudaErrorInvalidDevice behind), so that the cudaGetLastError() after it reports this launch only.
 #ifndef SSE_LAUNCH_KERNEL
-#define SSE_LAUNCH_KERNEL(kern, grid, block, smem_bytes, stream, ...) kern<<<grid, block, smem_bytes, stream>>>(__VA_ARGS__)
+#define SSE_LAUNCH_KERNEL(kern, grid, block, smem_bytes, stream, ...) \
+    do {                                                              \
+        (void)cudaGetLastError();                                     \
+        kern<<<grid, block, smem_bytes, stream>>>(__VA_ARGS__);       \
+    } while (0)
 #endif
 
 namespace {
@@ -164,9 +170,12 @@ int32_t sweep_shape(const sse_walkers *w, SweepShape &sh) {
     const int W = w->dw.W, N = m->dm.n_sites;
     sh.grid = std::min(W, m->n_sm);
     sh.nloc_max = (W + sh.grid - 1) / sh.grid;
-    int ww = w->worm_warps > 0 ? w->worm_warps : std::min(8, (sh.nloc_max + 31) / 32);
-    int sw = w->stream_warps > 0 ? w->stream_warps : std::min(SWEEP_MAX_WARPS - ww, std::max(1, sh.nloc_max));
-    if (ww < 1 || sw < 1 || ww + sw > SWEEP_MAX_WARPS) return fail("launch shape: need 1 <= worm_warps, 1 <= stream_warps, worm_warps + stream_warps <= 16");
+    const int ww_max = SPLIT_REGS ? WORM_GROUP_WARPS : std::min(8, SWEEP_MAX_WARPS - 1);
+    int ww = w->worm_warps > 0 ? w->worm_warps : std::min(ww_max, (sh.nloc_max + 31) / 32);
+    const int sw_max = SPLIT_REGS ? STREAM_GROUP_WARPS : SWEEP_MAX_WARPS - ww;
+    int sw = w->stream_warps > 0 ? w->stream_warps : std::min(sw_max, std::max(1, sh.nloc_max));
+    if (ww < 1 || sw < 1 || ww > ww_max || sw > sw_max)
+        return fail("launch shape: need 1 <= worm_warps <= " + std::to_string(ww_max) + " and 1 <= stream_warps <= " + std::to_string(sw_max));
     const int budget = 227 * 1024 - 1024;
     const int fixed = m->dm.tl.bytes + sched_bytes(sh.nloc_max);
     // stream warps keep state[] and mark[] (level 1) and vlast[] (level 2) of their walker in shared memory.  The number
@@ -206,7 +215,7 @@ int32_t launch_sweep(sse_walkers *w, int n_sweeps, unsigned long long budget, in
     a.stream_warps = sh.stream_warps;
     a.level = sh.level;
     a.nloc_max = sh.nloc_max;
-    const int block = (sh.worm_warps + sh.stream_warps) * 32;
+    const int block = (SPLIT_REGS ? SWEEP_MAX_WARPS : sh.worm_warps + sh.stream_warps) * 32;
     if (sh.smem > 48 * 1024) {
         CU(cudaFuncSetAttribute(k_sweep<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh.smem));
         CU(cudaFuncSetAttribute(k_sweep<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh.smem));
@@ -833,6 +842,7 @@ int32_t sse_comm_init(sse_walkers *w, const sse_nccl_id *id, int32_t rank, int32
     CU(cudaSetDevice(w->model->device));
     if (w->comm) { nccl().CommDestroy(w->comm); w->comm = nullptr; }
     NC(nccl().CommInitRank(&w->comm, nranks, *id, rank));
+    (void)cudaGetLastError();
     w->comm_rank = rank;
     w->comm_nranks = nranks;
     return 0;

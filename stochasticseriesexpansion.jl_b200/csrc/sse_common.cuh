@@ -45,10 +45,30 @@ constexpr uint32_t VMASK = ((1u << VBITS) - 1u) << 2;  // bits 2..13
 constexpr int BOND_SHIFT = 2 + VBITS;                  // 14
 constexpr int RNG_WORDS = 66;                          // 33 Philox blocks x 2 draws (see phase_diag_build)
 constexpr int PHASE_WARPS = 4;                         // warps per CTA of sse::k_phase (one warp = one walker)
+// CTA shape of sse::k_sweep.  Default: 24 warps = 8 worm warps + 16 stream warps, launched at 80 registers per thread;
+// the two roles then re-balance the register file with setmaxnreg (Hopper/Blackwell): the worm warpgroups shrink to
+// WORM_REGS, the stream warpgroups grow to STREAM_REGS (8*32*48 + 16*32*96 = 768*80: the CTA's allocation exactly).  The worm
+// chase needs few registers but many lanes, the streaming pass needs ~100 registers and as many warps as possible.
+// SSE_SWEEP_SPLIT_REGS=0 builds the plain variant (SSE_SWEEP_MAX_WARPS warps, roles contiguous, one register budget).
+#ifndef SSE_SWEEP_SPLIT_REGS
+#define SSE_SWEEP_SPLIT_REGS 1
+#endif
+#if SSE_SWEEP_SPLIT_REGS
+constexpr bool SPLIT_REGS = true;
+constexpr int WORM_GROUP_WARPS = 8, STREAM_GROUP_WARPS = 16;
+constexpr int SWEEP_MAX_WARPS = WORM_GROUP_WARPS + STREAM_GROUP_WARPS;
+#define SSE_WORM_REGS 48
+#define SSE_STREAM_REGS 96
+#else
 #ifndef SSE_SWEEP_MAX_WARPS
 #define SSE_SWEEP_MAX_WARPS 16
 #endif
-constexpr int SWEEP_MAX_WARPS = SSE_SWEEP_MAX_WARPS;   // warps per CTA of sse::k_sweep (16: launch bounds 512 x 1 = 128 registers per thread)
+constexpr bool SPLIT_REGS = false;
+constexpr int SWEEP_MAX_WARPS = SSE_SWEEP_MAX_WARPS;   // 16: launch bounds 512 x 1 = 128 registers per thread
+constexpr int WORM_GROUP_WARPS = 8, STREAM_GROUP_WARPS = SWEEP_MAX_WARPS - 1;
+#define SSE_WORM_REGS 128
+#define SSE_STREAM_REGS 128
+#endif
 constexpr int ROT_MARGIN = 224;                        // ring slack between the write head and unread old records (>= 32 * (OP_AHEAD + 2))
 
 __host__ __device__ __forceinline__ uint32_t op_pack(uint32_t bond, uint32_t gv, uint32_t diag) {
@@ -209,6 +229,11 @@ __device__ __forceinline__ void cp_async16(uint32_t dst_s, const void *src, bool
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+// register re-balancing between the warpgroups of a CTA (every warp of a warpgroup must execute the same one)
+template <int N>
+__device__ __forceinline__ void regs_shrink() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N>
+__device__ __forceinline__ void regs_grow() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 __device__ __forceinline__ uint32_t lds32(uint32_t a) {
     uint32_t v;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");

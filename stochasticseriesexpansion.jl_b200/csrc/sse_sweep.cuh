@@ -294,7 +294,21 @@ __global__ void __launch_bounds__(SWEEP_MAX_WARPS * 32, 1) k_sweep(const DevMode
     }
     __syncthreads();
 
-    if (warp < a.worm_warps) {
+    if (SPLIT_REGS) {
+        // warps [0, 8) form the two worm warpgroups, warps [8, 24) the four stream warpgroups; a.worm_warps / a.stream_warps
+        // of them are active (the others only take part in the register hand-over and leave)
+        if (warp < WORM_GROUP_WARPS) {
+            regs_shrink<SSE_WORM_REGS>();
+            if (warp < a.worm_warps) worm_warp_role<INJ>(st, dm, dw, a, sched, nloc, warp, lane);
+        } else {
+            regs_grow<SSE_STREAM_REGS>();
+            const int sw = warp - WORM_GROUP_WARPS;
+            if (sw < a.stream_warps) {
+                uint8_t *scratch = smem + dm.tl.bytes + sched_bytes(a.nloc_max) + (size_t)sw * stream_scratch_bytes(dm.n_sites, a.level);
+                stream_warp_role<INJ>(st, dm, dw, a, sched, nloc, scratch, lane);
+            }
+        }
+    } else if (warp < a.worm_warps) {
         worm_warp_role<INJ>(st, dm, dw, a, sched, nloc, warp, lane);
     } else if (warp < a.worm_warps + a.stream_warps) {
         uint8_t *scratch = smem + dm.tl.bytes + sched_bytes(a.nloc_max) +

@@ -297,6 +297,10 @@ static inline void cp_async16(uint32_t dst_s, const void *src, bool pred) {
 static inline void cp_async_commit() {}
 template <int N>
 static inline void cp_async_wait() {}
+template <int N>
+static inline void regs_shrink() {}
+template <int N>
+static inline void regs_grow() {}
 static inline uint32_t lds32(uint32_t a) { return *reinterpret_cast<const uint32_t *>(emu_smem_at(a, 4)); }
 }  // namespace sse
 

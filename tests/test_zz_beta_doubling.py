@@ -224,7 +224,7 @@ def test_gpu_full_size_parity(shape):
 @pytest.mark.gpu
 def test_gpu_full_size_parity_config2():
     """BASELINE.json configs[2]: L = beta = 64 (4096 sites, n ~ 3.7e5 records, M ~ 9e5 slots, ~8.7e5 worm visits per sweep)."""
-    gw = _body_full_size_parity(64, 64, 6)
+    gw = _body_full_size_parity(64, 64, 6, per_level=6)
     assert gw.num_operators().min() > 3.5e5
 
 
@@ -237,7 +237,8 @@ def test_gpu_full_size_parity_config4():
     L, beta = 48, 48
     model = dimer_bilayer(L)
     # measured on the oracle at L = 6 and 8: n ~ 2.7 operators and M ~ 7.6 slots per bond and unit of beta
-    _body_full_size_parity(L, beta, 5, model=model, n_est=2.9 * beta * 2 * L * L, per_level=3, walkers=2)
+    # 8 sweeps per level: with fewer the worm-count controller has not converged and a sweep costs 4e7 visits instead of 3e6
+    _body_full_size_parity(L, beta, 5, model=model, n_est=2.9 * beta * 2 * L * L, per_level=8, walkers=2)
 
 
 def _body_bani_cold_task(L, T, walkers, sweeps, budget, launches):
@@ -279,5 +280,5 @@ def test_emu_bani_cold_task(emu):
 
 @pytest.mark.gpu
 def test_gpu_bani_cold_task():
-    done = _body_bani_cold_task(20, 0.05, 64, 20, 1_000_000, 12)
-    assert done.max() >= 20
+    done = _body_bani_cold_task(20, 0.05, 64, 8, 1_000_000, 12)
+    assert done.max() >= 8

@@ -63,14 +63,14 @@ def _body_switching_keeps_the_trajectory():
     b = Walkers(dm, Ts, m_capacity=4096, seed=12)
     a.init()
     b.init()
-    for shape in ((1, 1), (3, 2), (0, 0), (1, 15), (8, 8)):
+    for shape in ((1, 1), (3, 2), (0, 0), (1, 15), (8, 8), (8, 16)):
         b.set_launch_shape(*shape)
         a.sweep(4)
         b.sweep(4)
     for i in range(len(Ts)):
         G._same_state(a.get_state(i), b.get_state(i), f"walker {i}")
     with pytest.raises(SSEError):
-        b.set_launch_shape(12, 5)
+        b.set_launch_shape(12, 30)
 
 
 def _body_many_walkers_per_lane(monkeypatch):
