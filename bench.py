@@ -412,7 +412,7 @@ def secondary_config1(args, dev_index, stream):
     a = copy.copy(args)
     a.L, a.beta, a.beta_doublings, a.therm, a.m_capacity, a.n_capacity = 32, 32.0, 5, 20, 0, 0
     wk, dm, T, W, t_setup = setup_walkers(a, dev_index, 0, 4096, stream.cuda_stream)
-    B = 300000
+    B = 400000
     wk.advance(B, thermalized=True)
     wk.fetch_counters(reset=True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -441,8 +441,8 @@ def main():
     ap.add_argument("--beta", type=float, default=64.0)
     ap.add_argument("--walkers", type=int, default=0, help="walkers per GPU; 0 = as many as the GPU's memory holds")
     ap.add_argument("--max-walkers", type=int, default=0)
-    ap.add_argument("--visits-per-step", type=float, default=1.5e6,
-                    help="worm visits every walker does per step (one sse_advance launch); ~2 sweeps at L = beta = 64")
+    ap.add_argument("--visits-per-step", type=float, default=3.0e6,
+                    help="worm visits every walker does per step (one sse_advance launch); ~3.5 sweeps at L = beta = 64")
     ap.add_argument("--worm-warps", type=int, default=0)
     ap.add_argument("--stream-warps", type=int, default=0)
     ap.add_argument("--therm", type=int, default=12, help="sweeps at the target temperature after the doubling levels")

@@ -45,20 +45,22 @@ constexpr uint32_t VMASK = ((1u << VBITS) - 1u) << 2;  // bits 2..13
 constexpr int BOND_SHIFT = 2 + VBITS;                  // 14
 constexpr int RNG_WORDS = 66;                          // 33 Philox blocks x 2 draws (see phase_diag_build)
 constexpr int PHASE_WARPS = 4;                         // warps per CTA of sse::k_phase (one warp = one walker)
-// CTA shape of sse::k_sweep.  Default: 24 warps = 8 worm warps + 16 stream warps, launched at 80 registers per thread;
-// the two roles then re-balance the register file with setmaxnreg (Hopper/Blackwell): the worm warpgroups shrink to
-// WORM_REGS, the stream warpgroups grow to STREAM_REGS (8*32*48 + 16*32*96 = 768*80: the CTA's allocation exactly).  The worm
-// chase needs few registers but many lanes, the streaming pass needs ~100 registers and as many warps as possible.
-// SSE_SWEEP_SPLIT_REGS=0 builds the plain variant (SSE_SWEEP_MAX_WARPS warps, roles contiguous, one register budget).
+// CTA shape of sse::k_sweep.  Default: 16 warps (launch bounds 512 x 1 = 128 registers per thread), roles contiguous.
+// SSE_SWEEP_SPLIT_REGS=1 builds the setmaxnreg variant: 24 warps = 8 worm warps + 16 stream warps launched at 80 registers;
+// the worm warpgroups shrink to SSE_WORM_REGS, the stream warpgroups grow to SSE_STREAM_REGS (8*32*48 + 16*32*96 = 768*80).
+// Measured on B200 (profiles/r2_l_l2policy_split.txt): the split loses 15-20 %, because at 48 registers the chase loop
+// spills onto its critical path and the extra stream warps add memory contention that lengthens every worm visit.
 #ifndef SSE_SWEEP_SPLIT_REGS
-#define SSE_SWEEP_SPLIT_REGS 1
+#define SSE_SWEEP_SPLIT_REGS 0
 #endif
 #if SSE_SWEEP_SPLIT_REGS
 constexpr bool SPLIT_REGS = true;
 constexpr int WORM_GROUP_WARPS = 8, STREAM_GROUP_WARPS = 16;
 constexpr int SWEEP_MAX_WARPS = WORM_GROUP_WARPS + STREAM_GROUP_WARPS;
+#ifndef SSE_WORM_REGS
 #define SSE_WORM_REGS 48
 #define SSE_STREAM_REGS 96
+#endif
 #else
 #ifndef SSE_SWEEP_MAX_WARPS
 #define SSE_SWEEP_MAX_WARPS 16
@@ -196,10 +198,27 @@ __device__ __forceinline__ uint4 lds128(uint32_t a) {
     asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
     return v;
 }
+// L2 eviction policies.  The record ring is touched in two ways: the worm phase reads and rewrites random sectors that
+// nobody needs again soon (evict_first), the record build writes records whose forward links are patched a few hundred
+// microseconds later (evict_last: a patch that finds its sector in L2 is merged there; one that does not costs a DRAM
+// read-modify-write — measured: as much DRAM traffic as the whole worm phase).
+__device__ __forceinline__ unsigned long long policy_evict_first() {
+    unsigned long long p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ unsigned long long policy_evict_last() {
+    unsigned long long p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
 // per-lane accesses of the worm phase: every lane touches its own walker
-__device__ __forceinline__ uint4 lane_ld128(const uint4 *p) {
+__device__ __forceinline__ uint4 lane_ld128(const uint4 *p, unsigned long long pol) {
     uint4 v;
-    asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    asm volatile("ld.global.cg.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "l"(p), "l"(pol)
+                 : "memory");
     return v;
 }
 __device__ __forceinline__ uint2 lane_ld64(const uint2 *p) {
@@ -207,8 +226,18 @@ __device__ __forceinline__ uint2 lane_ld64(const uint2 *p) {
     asm volatile("ld.global.cg.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ void lane_st32(void *p, uint32_t v) {
-    asm volatile("st.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+__device__ __forceinline__ void lane_st32(void *p, uint32_t v, unsigned long long pol) {
+    asm volatile("st.global.L2::cache_hint.u32 [%0], %1, %2;" ::"l"(p), "r"(v), "l"(pol) : "memory");
+}
+// stores of the record build
+__device__ __forceinline__ void st128_hint(uint4 *p, uint4 v, unsigned long long pol) {
+    asm volatile("st.global.L2::cache_hint.v4.u32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void st16_hint(void *p, uint32_t v, unsigned long long pol) {
+    asm volatile("st.global.L2::cache_hint.u16 [%0], %1, %2;" ::"l"(p), "h"((unsigned short)v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void st8_hint(void *p, uint32_t v, unsigned long long pol) {
+    asm volatile("st.global.L2::cache_hint.u8 [%0], %1, %2;" ::"l"(p), "r"(v), "l"(pol) : "memory");
 }
 __device__ __forceinline__ uint32_t ld_volatile_shared(const uint32_t *p) {
     return *reinterpret_cast<const volatile uint32_t *>(p);
@@ -218,9 +247,9 @@ __device__ __forceinline__ void backoff(unsigned ns) { __nanosleep(ns); }
 // Asynchronous global -> shared copies (LDGSTS) for the prefetch queues of the streaming pass: the data never sits in a
 // register while in flight, so no register move or scoreboard wait can stall on it, and the groups complete in order.
 // pred = false writes zeros without reading.
-__device__ __forceinline__ void cp_async4(uint32_t dst_s, const void *src, bool pred) {
+__device__ __forceinline__ void cp_async4(uint32_t dst_s, const void *src, bool pred, unsigned long long pol) {
     const int sz = pred ? 4 : 0;
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst_s), "l"(src), "r"(sz) : "memory");
+    asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 4, %2, %3;" ::"r"(dst_s), "l"(src), "r"(sz), "l"(pol) : "memory");
 }
 __device__ __forceinline__ void cp_async16(uint32_t dst_s, const void *src, bool pred) {
     const int sz = pred ? 16 : 0;
@@ -263,14 +292,14 @@ __host__ __device__ __forceinline__ uint4 rec_pack(uint32_t op, uint32_t l0, uin
 }
 // overwrite the leg link named by `target` (k << 2 | leg) of the generation at G with `value`: the 3-byte field starts
 // at byte 4 + 3*leg of the record, so it is one aligned 16-bit store and one byte store
-__device__ __forceinline__ void rec_patch(uint4 *rec, uint32_t G, uint32_t Rcap, uint32_t target, uint32_t value) {
+__device__ __forceinline__ void rec_patch(uint4 *rec, uint32_t G, uint32_t Rcap, uint32_t target, uint32_t value, unsigned long long pol) {
     uint8_t *b = reinterpret_cast<uint8_t *>(rec + ring(G, Rcap, target >> 2)) + 4u + 3u * (target & 3u);
     if (target & 1u) {  // odd offset: byte, then aligned half-word
-        b[0] = (uint8_t)value;
-        *reinterpret_cast<uint16_t *>(b + 1) = (uint16_t)(value >> 8);
+        st8_hint(b, value & 0xffu, pol);
+        st16_hint(b + 1, value >> 8, pol);
     } else {            // even offset: aligned half-word, then byte
-        *reinterpret_cast<uint16_t *>(b) = (uint16_t)value;
-        b[2] = (uint8_t)(value >> 16);
+        st16_hint(b, value & 0xffffu, pol);
+        st8_hint(b + 2, value >> 16, pol);
     }
 }
 

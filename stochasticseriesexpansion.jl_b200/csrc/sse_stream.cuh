@@ -44,6 +44,7 @@ struct OpReader {
     const uint2 *words;
     const uint4 *rec;
     uint32_t G, Rcap, lane, lt, ring_s;
+    unsigned long long pol;     // L2 policy of the op-code gathers: read once (evict_first)
     int nchunks, next_req;
     uint32_t wcur, wnext;       // bitmap words of the block of 32 chunks being requested from, and of the next block
     uint32_t kreq;              // first record of the next chunk to request
@@ -62,7 +63,7 @@ struct OpReader {
         if (c >= nchunks) bits = 0u;
         const bool have = (bits >> lane) & 1u;
         const uint32_t idx = have ? ring(G, Rcap, kreq + __popc(bits & lt)) : 0u;
-        cp_async4(ring_s + 4u * (32u * (uint32_t)(c & (OP_RING - 1)) + lane), &rec[idx].x, have);
+        cp_async4(ring_s + 4u * (32u * (uint32_t)(c & (OP_RING - 1)) + lane), &rec[idx].x, have, pol);
         kreq += __popc(bits);
 #pragma unroll
         for (int i = 0; i < OP_RING; ++i)
@@ -77,6 +78,7 @@ struct OpReader {
         lane = lane_;
         lt = lanemask_lt();
         ring_s = ring_s_;
+        pol = policy_evict_first();
         nchunks = nchunks_;
         next_req = 0;
         wcur = word_at((int)lane);
@@ -128,6 +130,7 @@ constexpr uint32_t BUILD_QUEUE = 64;  // entries; at most 31 waiting + 32 new on
 // different places, and a loop body beyond the 32 KB instruction cache made instruction fetch the bottleneck of the
 // whole pass (measured: ~1 instruction per cycle and SM however many warps streamed).
 struct BuildArgs {
+    unsigned long long pol;  // L2 policy of the record stores and link patches (evict_last)
     uint32_t *queue;
     uint8_t *mark;
     uint32_t *vfirst, *vlast;
@@ -135,9 +138,19 @@ struct BuildArgs {
     uint32_t Rcap, Gn, lane;
 };
 
-// the nearest earlier / later operator on a contested site, searched among the group's operators (rare)
-__device__ __noinline__ void build_resolve_collisions(uint32_t inv_mask, uint32_t k0, uint32_t lane, bool nn, uint32_t sa, uint32_t sb,
-                                                      uint32_t &pa, uint32_t &pb, uint32_t &sua, uint32_t &sub) {
+// The links are built WITHOUT touching a record twice at random.  A first version patched the forward link of the previous
+// operator on a site when the next one came by (as make_vertex_list! does, vertex_list.jl:36-38): 2 scattered partial
+// stores per operator into sectors written ~N/2 records earlier, which had usually left L2 by then — a DRAM
+// read-modify-write each, as much DRAM traffic as the whole worm phase (ncu: 97 of 251 GB per launch).  Instead:
+//   forward  (build_records, slot order):   record k = {op, backward links}, the previous operator on each site from vlast[];
+//   backward (finish_links, reverse order): forward links from vnext[site] = first leg of the next operator on the site,
+//                                           which is known because the later records were handled first.
+// Both passes read and write the ring sequentially.  vnext[] lives in the vfirst[] array: it starts as vfirst (the world
+// line is periodic: after the last operator comes the first, vertex_list.jl:46-51) and ends as vfirst again.
+
+// nearest earlier (pa/pb: its top leg) operator of the group on each of a lane's sites, and whether a later one exists
+__device__ __noinline__ void group_resolve_earlier(uint32_t inv_mask, uint32_t k0, uint32_t lane, bool nn, uint32_t sa, uint32_t sb,
+                                                   uint32_t &pa, uint32_t &pb, bool &later_a, bool &later_b) {
     for (uint32_t mm = inv_mask; mm;) {
         const int L = __ffs(mm) - 1;
         mm &= mm - 1;
@@ -149,12 +162,47 @@ __device__ __noinline__ void build_resolve_collisions(uint32_t inv_mask, uint32_
             if (sb == qa) pb = qk | 2u;
             if (sb == qb) pb = qk | 3u;
         } else if (nn && (int)lane < L) {
-            if (sua == NONE24) { if (sa == qa) sua = qk; else if (sa == qb) sua = qk | 1u; }
-            if (sub == NONE24) { if (sb == qa) sub = qk; else if (sb == qb) sub = qk | 1u; }
+            if (sa == qa || sa == qb) later_a = true;
+            if (sb == qa || sb == qb) later_b = true;
         }
     }
 }
+// nearest later (sua/sub: its bottom leg) operator of the group on each of a lane's sites, and whether an earlier one exists
+__device__ __noinline__ void group_resolve_later(uint32_t inv_mask, uint32_t k0, uint32_t lane, bool nn, uint32_t sa, uint32_t sb,
+                                                 uint32_t &sua, uint32_t &sub, bool &earlier_a, bool &earlier_b) {
+    for (uint32_t mm = inv_mask; mm;) {
+        const int L = __ffs(mm) - 1;
+        mm &= mm - 1;
+        const uint32_t qa = __shfl_sync(FULL, sa, L), qb = __shfl_sync(FULL, sb, L);
+        const uint32_t qk = (k0 + (uint32_t)L) << 2;
+        if (nn && (int)lane < L) {
+            if (sua == NONE24) { if (sa == qa) sua = qk; else if (sa == qb) sua = qk | 1u; }
+            if (sub == NONE24) { if (sb == qa) sub = qk; else if (sb == qb) sub = qk | 1u; }
+        } else if (nn && (int)lane > L) {
+            if (sa == qa || sa == qb) earlier_a = true;
+            if (sb == qa || sb == qb) earlier_b = true;
+        }
+    }
+}
+// operators of the group that share a site with another one: every operator tags its two sites, a lost tag reveals a
+// collision, the losers flag the contested sites, and every operator on a flagged site takes part in the search
+__device__ __forceinline__ uint32_t group_collisions(uint8_t *mark, uint32_t lane, bool nn, uint32_t sa, uint32_t sb) {
+    if (nn) {
+        mark[sa] = (uint8_t)lane;
+        mark[sb] = (uint8_t)lane;
+    }
+    __syncwarp();
+    const bool lost_a = nn && mark[sa] != (uint8_t)lane, lost_b = nn && mark[sb] != (uint8_t)lane;
+    if (!__ballot_sync(FULL, lost_a || lost_b)) return 0u;
+    __syncwarp();
+    if (lost_a) mark[sa] = 0x7f;
+    if (lost_b) mark[sb] = 0x7f;
+    __syncwarp();
+    const bool inv = nn && (mark[sa] == 0x7f || mark[sb] == 0x7f);
+    return __ballot_sync(FULL, inv);
+}
 
+// forward pass: records k0 .. k0+m-1 = {op code, backward links} from the warp's queue {op code, site a, site b}
 __device__ __noinline__ void build_records(const BuildArgs b, uint32_t k0, uint32_t m) {
     const uint32_t lane = b.lane, Rcap = b.Rcap, Gn = b.Gn;
     const bool nn = lane < m;
@@ -165,24 +213,10 @@ __device__ __noinline__ void build_records(const BuildArgs b, uint32_t k0, uint3
         sa = b.queue[BUILD_QUEUE + q];
         sb = b.queue[2 * BUILD_QUEUE + q];
     }
-    // same-site collisions inside the group are rare: every operator tags its two sites, a lost tag
-    // reveals a collision, and only then the nearest earlier / later operator on each site is searched
-    uint32_t pa = NONE24, pb = NONE24, sua = NONE24, sub = NONE24;
-    if (nn) {
-        b.mark[sa] = (uint8_t)lane;
-        b.mark[sb] = (uint8_t)lane;
-    }
-    __syncwarp();
-    const bool lost_a = nn && b.mark[sa] != (uint8_t)lane, lost_b = nn && b.mark[sb] != (uint8_t)lane;
-    if (__ballot_sync(FULL, lost_a || lost_b)) {
-        // losers flag the contested sites; every operator on a flagged site takes part in the search
-        __syncwarp();
-        if (lost_a) b.mark[sa] = 0x7f;
-        if (lost_b) b.mark[sb] = 0x7f;
-        __syncwarp();
-        const bool inv = nn && (b.mark[sa] == 0x7f || b.mark[sb] == 0x7f);
-        build_resolve_collisions(__ballot_sync(FULL, inv), k0, lane, nn, sa, sb, pa, pb, sua, sub);
-    }
+    uint32_t pa = NONE24, pb = NONE24;
+    bool later_a = false, later_b = false;
+    const uint32_t inv = group_collisions(b.mark, lane, nn, sa, sb);
+    if (inv) group_resolve_earlier(inv, k0, lane, nn, sa, sb, pa, pb, later_a, later_b);
     uint32_t ma = NONE32, mb = NONE32;
     if (nn) {
         if (pa == NONE24) ma = b.vlast[sa];
@@ -191,20 +225,68 @@ __device__ __noinline__ void build_records(const BuildArgs b, uint32_t k0, uint3
     __syncwarp();
     if (nn) {
         const uint32_t me = k << 2;
-        uint32_t bla = pa, blb = pb;
+        uint32_t bla = pa, blb = pb;  // NONE24 = first operator on the site: closed by finish_links
         if (pa == NONE24) {
-            if (ma != NONE32) { bla = ma; rec_patch(b.rec, Gn, Rcap, ma, me); }  // vertices[s1,p1] = (s,p) (vertex_list.jl:36-38)
-            else b.vfirst[sa] = me;                                               // vertex_list.jl:40
+            if (ma != NONE32) bla = ma;       // vertices[s,p] = (s1,p1) (vertex_list.jl:36-38)
+            else b.vfirst[sa] = me;           // vertex_list.jl:40
         }
         if (pb == NONE24) {
-            if (mb != NONE32) { blb = mb; rec_patch(b.rec, Gn, Rcap, mb, me | 1u); }
+            if (mb != NONE32) blb = mb;
             else b.vfirst[sb] = me | 1u;
         }
-        if (sua == NONE24) b.vlast[sa] = me | 2u;  // vertex_list.jl:42
-        if (sub == NONE24) b.vlast[sb] = me | 3u;
-        b.rec[ring(Gn, Rcap, k)] = rec_pack(newop, bla, blb, sua, sub);  // forward links still unknown stay NONE24 until patched
+        if (!later_a) b.vlast[sa] = me | 2u;  // vertex_list.jl:42
+        if (!later_b) b.vlast[sb] = me | 3u;
+        st128_hint(b.rec + ring(Gn, Rcap, k), rec_pack(newop, bla, blb, NONE24, NONE24), b.pol);
     }
     __syncwarp();
+}
+
+// backward pass over the n records of the new generation: forward links, and the periodic closure of the world lines
+__device__ __noinline__ void finish_links(const BuildArgs b, const uint4 *bond_info, uint32_t n, unsigned long long pol_final) {
+    const uint32_t lane = b.lane, Rcap = b.Rcap, Gn = b.Gn;
+    uint32_t *vnext = b.vfirst;
+    uint32_t k_hi = n;
+    // the records of the last group are requested one group ahead
+    uint32_t k0 = k_hi > 32u ? k_hi - 32u : 0u, m = k_hi - k0;
+    uint4 R = make_uint4(0, 0, 0, 0);
+    if (lane < m) R = __ldcg(b.rec + ring(Gn, Rcap, k0 + lane));
+    while (k_hi > 0u) {
+        const bool nn = lane < m;
+        const uint32_t k = k0 + lane;
+        const uint4 Rc = R;
+        const uint32_t nk_hi = k0, nk0 = nk_hi > 32u ? nk_hi - 32u : 0u, nm = nk_hi - nk0;
+        if (lane < nm) R = __ldcg(b.rec + ring(Gn, Rcap, nk0 + lane));  // next (earlier) group
+        uint32_t sa = 0, sb = 0;
+        if (nn) {
+            const uint4 bi = __ldg(bond_info + op_bond(Rc.x));
+            sa = bi.x & NONE24;
+            sb = bi.y & NONE24;
+        }
+        uint32_t sua = NONE24, sub = NONE24;
+        bool earlier_a = false, earlier_b = false;
+        const uint32_t inv = group_collisions(b.mark, lane, nn, sa, sb);
+        if (inv) group_resolve_later(inv, k0, lane, nn, sa, sb, sua, sub, earlier_a, earlier_b);
+        uint32_t na = 0, nb = 0;
+        if (nn) {
+            if (sua == NONE24) na = vnext[sa];
+            if (sub == NONE24) nb = vnext[sb];
+        }
+        __syncwarp();
+        if (nn) {
+            uint32_t bla = rec_link(Rc, 0), blb = rec_link(Rc, 1);
+            if (bla == NONE24) bla = b.vlast[sa];  // first operator on the site: its lower neighbour is the last one (vertex_list.jl:46-51)
+            if (blb == NONE24) blb = b.vlast[sb];
+            if (sua == NONE24) sua = na;
+            if (sub == NONE24) sub = nb;
+            if (!earlier_a) vnext[sa] = k << 2;
+            if (!earlier_b) vnext[sb] = (k << 2) | 1u;
+            st128_hint(b.rec + ring(Gn, Rcap, k), rec_pack(Rc.x, bla, blb, sua, sub), pol_final);
+        }
+        __syncwarp();
+        k_hi = nk_hi;
+        k0 = nk0;
+        m = nm;
+    }
 }
 
 // The in-order recurrence of the accept tests (sse.jl:164-166,176-178) for a chunk in which the bound test left some lane
@@ -377,6 +459,7 @@ __device__ void phase_diag_build(const SmTab &st, const DevModel &dm, const DevW
     double pm_lo = 0, pm_hi = 0, rm_sure = 0, rm_maybe = 0;
 
     BuildArgs ba;
+    ba.pol = policy_evict_last();
     ba.queue = c.queue;
     ba.mark = c.mark;
     ba.vfirst = c.vfirst;
@@ -563,16 +646,7 @@ __device__ void phase_diag_build(const SmTab &st, const DevModel &dm, const DevW
         build_records(ba, built, m);
         built += m;
     }
-    // periodic closure (vertex_list.jl:46-51)
-    for (int s = lane; s < N; s += 32) {
-        const uint32_t f = c.vfirst[s];
-        if (f != NONE32) {
-            const uint32_t l = c.vlast[s];
-            rec_patch(c.rec, Gn, Rcap, f, l);
-            rec_patch(c.rec, Gn, Rcap, l, f);
-        }
-    }
-    __syncwarp();
+    finish_links(ba, dm.bond_info, kbase, policy_evict_first());
     if (MEAS) {  // ---- measurement, part 3: the observables (sse.jl:73-82; result, magnetization_estimator.jl:205-230) ----
         const double sign = (neg & 1u) ? -1.0 : 1.0;  // sse.jl:313
         if (lane == 0) {

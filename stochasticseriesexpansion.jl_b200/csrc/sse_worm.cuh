@@ -30,6 +30,7 @@ struct WormLane {
 };
 
 struct LaneEnv {  // launch constants of the worm lanes
+    unsigned long long pol;  // L2 policy of the record accesses (evict_first)
     uint32_t t1_s, outc_s, maxw4, Rcap;
     unsigned long long seed;
     long long inj_len;
@@ -38,6 +39,7 @@ struct LaneEnv {  // launch constants of the worm lanes
 
 __device__ __forceinline__ LaneEnv lane_env(const SmTab &st, const DevModel &dm, const DevWalkers &dw) {
     LaneEnv e;
+    e.pol = policy_evict_first();
     e.t1_s = st.t1_s;
     e.outc_s = st.outc_s;
     e.maxw4 = (uint32_t)dm.max_worm * 4u;
@@ -95,7 +97,7 @@ __device__ __forceinline__ void lane_open(const DevWalkers &dw, int w, WormLane 
 // resume a parked worm: request its current record again
 __device__ __forceinline__ void lane_resume(const LaneEnv &e, WormLane &L) {
     L.cur = L.rec + ring(L.G, e.Rcap, L.pos >> 2);
-    L.R = lane_ld128(L.cur);
+    L.R = lane_ld128(L.cur, e.pol);
 }
 // Give the walker back: stream position, sweep progress and (inworm) the worm in flight.
 __device__ __forceinline__ void lane_store(const DevWalkers &dw, int w, const WormLane &L, uint32_t inworm, uint32_t extra_flags) {
@@ -139,7 +141,7 @@ __device__ __forceinline__ bool lane_pick_start(const LaneEnv &e, WormLane &L) {
     L.pos0 = (k0 << 2) | l0;
     L.pos = L.pos0;
     L.cur = L.rec + ring(L.G, e.Rcap, k0);
-    L.R = lane_ld128(L.cur);
+    L.R = lane_ld128(L.cur, e.pol);
     const uint4 bi = __ldg(e.bond_info + op_bond(L.R.x));
     const uint32_t dim0 = (l0 & 1u) ? (bi.y >> 24) : (bi.x >> 24);                // site_of_leg (sse.jl:250)
     L.w0 = 1u + (uint32_t)sse_uint_below(lane_draw<INJ>(e, L), dim0 - 1u);        // sse.jl:251
@@ -153,7 +155,7 @@ __device__ __forceinline__ void lane_set_start(const LaneEnv &e, WormLane &L, ui
     L.pos0 = (k0 << 2) | l0;
     L.pos = L.pos0;
     L.cur = L.rec + ring(L.G, e.Rcap, k0);
-    L.R = lane_ld128(L.cur);
+    L.R = lane_ld128(L.cur, e.pol);
     L.w0 = w0;
     L.wf = w0;
     L.len = 1;
@@ -182,10 +184,10 @@ __device__ __forceinline__ bool lane_visit(const LaneEnv &e, WormLane &L) {
     const uint32_t leg_out = (t.z >> 16) & 3u;
     const uint32_t posn = rec_link(Rc, leg_out);  // (leg_in, p) = vertices[leg_out, p] (sse.jl:295)
     uint4 *const nxt = L.rec + ring(L.G, e.Rcap, posn >> 2);
-    L.R = lane_ld128(nxt);
+    L.R = lane_ld128(nxt, e.pol);
     // ---- everything below overlaps with the load ----
     const uint32_t newop = (x & ~(VMASK | 2u)) | (t.z & (VMASK | 2u));  // OperCode(bond, new_vertex) (sse.jl:285)
-    lane_st32(L.cur, newop);
+    lane_st32(L.cur, newop, e.pol);
     const uint32_t w_out = t.z >> 24, dim_out = t.w >> 24;
     const bool stop1 = (((pos & ~3u) | leg_out) == L.pos0) && (w_out + L.w0 == dim_out);  // sse.jl:288-290
     L.len += stop1 ? 0u : 1u;

@@ -256,15 +256,26 @@ static inline void emu_check_global(const void *p, size_t align) {
 static inline uint4 lds128(uint32_t a) { return *reinterpret_cast<const uint4 *>(emu_smem_at(a, 16)); }
 // Per-lane accesses of the worm phase (every lane touches its own walker), the volatile status words of the
 // scheduler, and the back-off of a polling loop (a yield: fibers only switch at collectives otherwise).
-static inline uint4 lane_ld128(const uint4 *p) {
+static inline unsigned long long policy_evict_first() { return 1; }
+static inline unsigned long long policy_evict_last() { return 2; }
+static inline uint4 lane_ld128(const uint4 *p, unsigned long long) {
     emu_check_global(p, 16);
     return *p;
 }
+static inline void st128_hint(uint4 *p, uint4 v, unsigned long long) {
+    emu_check_global(p, 16);
+    *p = v;
+}
+static inline void st16_hint(void *p, uint32_t v, unsigned long long) {
+    emu_check_global(p, 2);
+    *reinterpret_cast<uint16_t *>(p) = (uint16_t)v;
+}
+static inline void st8_hint(void *p, uint32_t v, unsigned long long) { *reinterpret_cast<uint8_t *>(p) = (uint8_t)v; }
 static inline uint2 lane_ld64(const uint2 *p) {
     emu_check_global(p, 8);
     return *p;
 }
-static inline void lane_st32(void *p, uint32_t v) {
+static inline void lane_st32(void *p, uint32_t v, unsigned long long) {
     emu_check_global(p, 4);
     *reinterpret_cast<uint32_t *>(p) = v;
 }
@@ -278,7 +289,7 @@ static inline void st_volatile_shared(uint32_t *p, uint32_t v) {
 }
 static inline void backoff(unsigned) { emu::poll_yield(); }
 // asynchronous copies: performed at once (one legal timing); pred = false zero-fills
-static inline void cp_async4(uint32_t dst_s, const void *src, bool pred) {
+static inline void cp_async4(uint32_t dst_s, const void *src, bool pred, unsigned long long) {
     uint32_t v = 0;
     if (pred) {
         emu_check_global(src, 4);

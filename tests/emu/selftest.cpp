@@ -38,7 +38,7 @@ __global__ void k_mask_mismatch(uint32_t *out) {
 
 __global__ void k_oob(uint32_t *out) { out[64 + (threadIdx.x & 31u)] = 1; }  // allocation holds 64 words
 
-__global__ void k_misaligned(uint32_t *out) { (void)sse::lane_ld128(reinterpret_cast<const uint4 *>(out + 1)); }
+__global__ void k_misaligned(uint32_t *out) { (void)sse::lane_ld128(reinterpret_cast<const uint4 *>(out + 1), 0); }
 
 int main(int argc, char **argv) {
     const std::string c = argc > 1 ? argv[1] : "ok";

@@ -56,7 +56,7 @@ def test_emu_phase_parity_injected_stream(emu, name):
 
 @pytest.mark.parametrize("name", ["heisenberg_eof", "spin1_dz", "dimer_bilayer"])
 def test_emu_sweep_parity_philox(emu, name):
-    G.test_sweep_parity_philox(name)
+    G.test_sweep_parity_philox(name, W=10, therm=25, meas=10)  # the emulated "GPU" has 3 SMs: 3-4 walkers per CTA
 
 
 def test_emu_worm_traverse_reference_cases(emu):
@@ -85,36 +85,6 @@ def test_emu_api_errors_are_loud(emu):
 
 @pytest.mark.parametrize("level", [0, 1])
 def test_emu_large_lattice_memory_paths(emu, level, monkeypatch):
-    G.test_large_lattice_memory_paths(level, monkeypatch)
-
-
-# ---- 2 and 4 walkers per warp (sse::k_walkers_multi): same trajectories, bit for bit ----------------------------
-@pytest.fixture(params=[2, 4])
-def chains(request, monkeypatch):
-    monkeypatch.setenv("SSE_B200_CHAINS", str(request.param))
-    return request.param
-
-
-@pytest.mark.parametrize("k, name", [(2, "mixed_honeycomb"), (4, "heisenberg_eof")])
-def test_emu_multi_sweep_parity_philox(emu, monkeypatch, k, name):
-    monkeypatch.setenv("SSE_B200_CHAINS", str(k))
-    G.test_sweep_parity_philox(name)  # 33 walkers: the last warp is ragged for both 2 and 4 walkers per warp
-
-
-def test_emu_multi_edge_cases_empty_and_ragged_strings(emu, chains):
-    G.test_edge_cases_empty_and_ragged_strings()
-
-
-def test_emu_multi_checkpoint_roundtrip_and_pt_hooks(emu, chains):
-    G.test_checkpoint_roundtrip_and_pt_hooks()
-
-
-def test_emu_multi_overflow_is_loud(emu, chains):
-    G.test_overflow_is_loud()
-
-
-@pytest.mark.parametrize("level", [0, 1])
-def test_emu_multi_large_lattice_memory_paths(emu, chains, level, monkeypatch):
     G.test_large_lattice_memory_paths(level, monkeypatch)
 
 

@@ -117,25 +117,24 @@ def test_phase_parity_injected_stream(name):
 
 
 @pytest.mark.parametrize("name", list(MODEL_CLASSES))
-def test_sweep_parity_philox(name):
+def test_sweep_parity_philox(name, W=33, therm=40, meas=25):
     """Whole runs (init! + thermalisation with string growth + measured sweeps) agree exactly with the oracle
     when both draw from the Philox stream of the same (seed, walker id)."""
     model = MODEL_CLASSES[name]()
     dm, om = _pair(model)
-    W = 33
     Ts = np.linspace(0.15, 1.5, W)
     gw = Walkers(dm, Ts, m_capacity=8192, seed=4242, walker_id_offset=7)
     gw.init()
-    gw.sweep(40, thermalized=False)
-    gw.sweep(25, thermalized=True, measure=True)
+    gw.sweep(therm, thermalized=False)
+    gw.sweep(meas, thermalized=True, measure=True)
     sums, counts = gw.fetch_accumulators()
     cnt = gw.fetch_counters()
     visits = 0
-    for i in (0, 1, 16, 32):
+    for i in (0, 1, W // 2, W - 1):
         ow = OracleWalker(om, float(Ts[i]), seed=4242, walker_id=7 + i)
         ow.init()
-        ow.sweep(40, thermalized=False)
-        ow.sweep(25, thermalized=True, measure=True)
+        ow.sweep(therm, thermalized=False)
+        ow.sweep(meas, thermalized=True, measure=True)
         st = ow.get_state()
         _same_state(gw.get_state(i), st, f"{name} walker {i}")
         assert isconsistent(st["operators"], st["state"], om.sse_data)
@@ -143,7 +142,7 @@ def test_sweep_parity_philox(name):
         assert np.array_equal(counts[i], ocounts)
         np.testing.assert_allclose(sums[i], osums, rtol=1e-12, atol=1e-300)
         # instantaneous measure! agrees too
-    assert cnt["sweeps"] == W * 65
+    assert cnt["sweeps"] == W * (therm + meas)
     assert (gw.get_flags() & 7).sum() == 0
 
 
