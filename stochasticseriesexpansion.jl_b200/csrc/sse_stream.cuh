@@ -24,11 +24,11 @@ __device__ __forceinline__ void fill_draws(const Ctx &c, unsigned long long j0) 
         reinterpret_cast<uint4 *>(c.rng)[c.lane] = make_uint4(b[0], b[1], b[2], b[3]);
     }
 }
-// Draw with absolute index k from the scratch filled by fill_draws(j0) (or from the injected stream).
+// Draw number `rel` of the scratch filled by fill_draws(j0), i.e. draw k = 2*j0 + rel of the stream (or of the injected one).
 template <bool INJ>
-__device__ __forceinline__ uint64_t scratch_draw(const Ctx &c, unsigned long long j0, unsigned long long k) {
+__device__ __forceinline__ uint64_t scratch_draw(const Ctx &c, uint32_t rel, unsigned long long k) {
     if (INJ) return (long long)k < c.inj_len ? (uint64_t)__ldg(c.inj + k) : 0ull;
-    return c.rng[k - 2ull * j0];
+    return c.rng[rel];
 }
 
 // Sequential reader of a walker's operator string: per 32-slot chunk every lane gets the op code of its slot (0 =
@@ -41,21 +41,24 @@ __device__ __forceinline__ uint64_t scratch_draw(const Ctx &c, unsigned long lon
 // groups per chunk, in that order; take() waits until the chunk's own group has landed.
 template <int EXTRA>
 struct OpReader {
-    const uint2 *words;
     const uint4 *rec;
-    uint32_t G, Rcap, lane, lt, ring_s;
+    const uint2 *words;
+    uint32_t G, Rcap, lane, lt;
+    uint32_t dst_s;             // shared-space address of this lane's word in slot 0 of the op-code ring
     unsigned long long pol;     // L2 policy of the op-code gathers: read once (evict_first)
     int nchunks, next_req;
-    uint32_t wcur, wnext;       // bitmap words of the block of 32 chunks being requested from, and of the next block
+    // bitmap words, one per lane: of the block of 32 chunks before the one being requested from, of that block, and of the
+    // next one (already requested).  take() lags request() by OP_AHEAD < 32 chunks, so its chunk is in wprev or wcur.
+    uint32_t wprev, wcur, wnext;
     uint32_t kreq;              // first record of the next chunk to request
     uint32_t kold;              // first record of the next chunk to take
-    uint32_t bits_ring[OP_RING];  // occupancy of the chunks in flight (indexed with unrolled selects: stays in registers)
 
     __device__ __forceinline__ uint32_t word_at(int ch) const { return ch < nchunks ? __ldcg(&words[ch].x) : 0u; }
     // request the next chunk (chunks are requested in order 0, 1, 2, ...); the caller commits the group
     __device__ __forceinline__ void request() {
         const int c = next_req++;
-        if ((c & 31) == 0 && c > 0) {  // c opens a new block: the old one is used up, the one after is requested
+        if ((c & 31) == 0 && c > 0) {  // c opens a new block: the one after it is requested
+            wprev = wcur;
             wcur = wnext;
             wnext = word_at(c + 32 + (int)lane);
         }
@@ -63,11 +66,8 @@ struct OpReader {
         if (c >= nchunks) bits = 0u;
         const bool have = (bits >> lane) & 1u;
         const uint32_t idx = have ? ring(G, Rcap, kreq + __popc(bits & lt)) : 0u;
-        cp_async4(ring_s + 4u * (32u * (uint32_t)(c & (OP_RING - 1)) + lane), &rec[idx].x, have, pol);
+        cp_async4(dst_s + 128u * (uint32_t)(c & (OP_RING - 1)), rec + idx, have, pol);
         kreq += __popc(bits);
-#pragma unroll
-        for (int i = 0; i < OP_RING; ++i)
-            if ((c & (OP_RING - 1)) == i) bits_ring[i] = bits;
     }
     __device__ __forceinline__ void init(const uint2 *words_, const uint4 *rec_, uint32_t G_, uint32_t Rcap_, int nchunks_,
                                          uint32_t lane_, uint32_t ring_s_) {
@@ -77,16 +77,15 @@ struct OpReader {
         Rcap = Rcap_;
         lane = lane_;
         lt = lanemask_lt();
-        ring_s = ring_s_;
+        dst_s = ring_s_ + 4u * lane_;
         pol = policy_evict_first();
         nchunks = nchunks_;
         next_req = 0;
+        wprev = 0;
         wcur = word_at((int)lane);
         wnext = word_at(32 + (int)lane);
         kreq = 0;
         kold = 0;
-#pragma unroll
-        for (int i = 0; i < OP_RING; ++i) bits_ring[i] = 0;
         for (int i = 0; i < OP_AHEAD; ++i) {  // the pipeline's lead: chunks 0 .. OP_AHEAD-1, with the group pattern of a chunk
             request();
             cp_async_commit();
@@ -98,11 +97,10 @@ struct OpReader {
     __device__ __forceinline__ uint32_t take(int ch, uint32_t &bits, uint32_t &op) {
         // groups committed after chunk ch's own: EXTRA of its iteration + (OP_AHEAD - 1) later chunks x (1 + EXTRA)
         cp_async_wait<EXTRA + (OP_AHEAD - 1) * (1 + EXTRA)>();
-        bits = 0;
-#pragma unroll
-        for (int i = 0; i < OP_RING; ++i)
-            if ((ch & (OP_RING - 1)) == i) bits = bits_ring[i];
-        op = lds32(ring_s + 4u * (32u * (uint32_t)(ch & (OP_RING - 1)) + lane));
+        // the requests are at chunk next_req - 1 = ch + OP_AHEAD - 1: same block as ch, or the one after
+        const uint32_t w = ((next_req - 1) >> 5) == (ch >> 5) ? wcur : wprev;
+        bits = __shfl_sync(FULL, w, ch & 31);
+        op = lds32(dst_s + 128u * (uint32_t)(ch & (OP_RING - 1)));
         const uint32_t k0 = kold;
         kold += __popc(bits);
         return k0;
@@ -142,7 +140,7 @@ struct BuildArgs {
 // operator on a site when the next one came by (as make_vertex_list! does, vertex_list.jl:36-38): 2 scattered partial
 // stores per operator into sectors written ~N/2 records earlier, which had usually left L2 by then — a DRAM
 // read-modify-write each, as much DRAM traffic as the whole worm phase (ncu: 97 of 251 GB per launch).  Instead:
-//   forward  (build_records, slot order):   record k = {op, backward links}, the previous operator on each site from vlast[];
+//   forward  (build_records, slot order):   record k = {op, backward links, site a, site b}, the previous operator on each site from vlast[];
 //   backward (finish_links, reverse order): forward links from vnext[site] = first leg of the next operator on the site,
 //                                           which is known because the later records were handled first.
 // Both passes read and write the ring sequentially.  vnext[] lives in the vfirst[] array: it starts as vfirst (the world
@@ -236,13 +234,14 @@ __device__ __noinline__ void build_records(const BuildArgs b, uint32_t k0, uint3
         }
         if (!later_a) b.vlast[sa] = me | 2u;  // vertex_list.jl:42
         if (!later_b) b.vlast[sb] = me | 3u;
-        st128_hint(b.rec + ring(Gn, Rcap, k), rec_pack(newop, bla, blb, NONE24, NONE24), b.pol);
+        // the two forward-link fields carry the operator's sites to the backward pass (saves its bond-table lookup)
+        st128_hint(b.rec + ring(Gn, Rcap, k), rec_pack(newop, bla, blb, sa, sb), b.pol);
     }
     __syncwarp();
 }
 
 // backward pass over the n records of the new generation: forward links, and the periodic closure of the world lines
-__device__ __noinline__ void finish_links(const BuildArgs b, const uint4 *bond_info, uint32_t n, unsigned long long pol_final) {
+__device__ __noinline__ void finish_links(const BuildArgs b, uint32_t n, unsigned long long pol_final) {
     const uint32_t lane = b.lane, Rcap = b.Rcap, Gn = b.Gn;
     uint32_t *vnext = b.vfirst;
     uint32_t k_hi = n;
@@ -256,12 +255,7 @@ __device__ __noinline__ void finish_links(const BuildArgs b, const uint4 *bond_i
         const uint4 Rc = R;
         const uint32_t nk_hi = k0, nk0 = nk_hi > 32u ? nk_hi - 32u : 0u, nm = nk_hi - nk0;
         if (lane < nm) R = __ldcg(b.rec + ring(Gn, Rcap, nk0 + lane));  // next (earlier) group
-        uint32_t sa = 0, sb = 0;
-        if (nn) {
-            const uint4 bi = __ldg(bond_info + op_bond(Rc.x));
-            sa = bi.x & NONE24;
-            sb = bi.y & NONE24;
-        }
+        const uint32_t sa = nn ? rec_link(Rc, 2) : 0u, sb = nn ? rec_link(Rc, 3) : 0u;  // left there by build_records
         uint32_t sua = NONE24, sub = NONE24;
         bool earlier_a = false, earlier_b = false;
         const uint32_t inv = group_collisions(b.mark, lane, nn, sa, sb);
@@ -377,17 +371,17 @@ __device__ __forceinline__ ChunkIn diag_stage_b(const DevModel &dm, const Ctx &c
         in.dgm = __ballot_sync(FULL, is_dg);
         const uint32_t D = 2u * __popc(in.idm) + __popc(in.dgm);
         if (D) {
-            const unsigned long long my = draws + 2u * __popc(in.idm & lt) + __popc(in.dgm & lt);
-            const unsigned long long j0 = draws >> 1;
+            const uint32_t rel = (uint32_t)(draws & 1ull) + 2u * __popc(in.idm & lt) + __popc(in.dgm & lt);  // index into the scratch
+            const unsigned long long j0 = draws >> 1, my = 2ull * j0 + rel;
             fill_draws<INJ>(c, j0);
             if (!INJ && (draws & 1ull) && D == 64u && lane == 0)  // the one draw beyond 32 blocks
                 philox_extra_block(c.seed, c.wid, j0 + 32, reinterpret_cast<uint4 *>(c.rng) + 32);
             __syncwarp();
             if (is_id) {
-                in.bond = sse_uint_below32(scratch_draw<INJ>(c, j0, my), (uint32_t)dm.n_bonds);  // rand(rng, 1:N_b) - 1 (sse.jl:152)
-                in.r = sse_u01(scratch_draw<INJ>(c, j0, my + 1));                                         // sse.jl:166
+                in.bond = sse_uint_below32(scratch_draw<INJ>(c, rel, my), (uint32_t)dm.n_bonds);  // rand(rng, 1:N_b) - 1 (sse.jl:152)
+                in.r = sse_u01(scratch_draw<INJ>(c, rel + 1u, my + 1));                                    // sse.jl:166
             } else if (is_dg) {
-                in.r = sse_u01(scratch_draw<INJ>(c, j0, my));                                             // sse.jl:178
+                in.r = sse_u01(scratch_draw<INJ>(c, rel, my));                                             // sse.jl:178
             }
             draws += D;
             __syncwarp();  // the scratch is refilled for the next chunk
@@ -445,7 +439,7 @@ __device__ void phase_diag_build(const SmTab &st, const DevModel &dm, const DevW
     const int M = c.M;
     const double p_make_bond_raw = (double)dm.n_bonds / c.T;   // sse.jl:147
     const double p_remove_bond_raw = c.T / (double)dm.n_bonds; // sse.jl:148
-    const uint32_t Rcap = c.Rcap, n_old = (uint32_t)c.n;
+    const uint32_t Rcap = c.Rcap, n_old = (uint32_t)c.n, n_cap32 = (uint32_t)dw.n_cap;
     const uint32_t Gn = ring(c.G, Rcap, n_old);  // the new generation starts right behind the old one
     int n = c.n;
     uint32_t kbase = 0, built = 0;  // operators of the new generation so far / already linked
@@ -617,8 +611,7 @@ __device__ void phase_diag_build(const SmTab &st, const DevModel &dm, const DevW
         const uint32_t cnt = __popc(nm);
         // capacity: n_cap records, and the write head must stay clear of old records that are not consumed yet (the
         // reader is up to OP_AHEAD + 2 chunks ahead of this point: ROT_MARGIN covers them)
-        if ((long long)kbase + cnt > dw.n_cap ||
-            (long long)n_old + kbase + cnt + ROT_MARGIN > (long long)Rcap + in.kold0) {
+        if (kbase + cnt > n_cap32 || n_old + kbase + cnt + (uint32_t)ROT_MARGIN > Rcap + in.kold0) {  // all below 2^24
             c.flags |= SSE_FLAG_N_OVERFLOW;
             return;
         }
@@ -646,7 +639,7 @@ __device__ void phase_diag_build(const SmTab &st, const DevModel &dm, const DevW
         build_records(ba, built, m);
         built += m;
     }
-    finish_links(ba, dm.bond_info, kbase, policy_evict_first());
+    finish_links(ba, kbase, policy_evict_first());
     if (MEAS) {  // ---- measurement, part 3: the observables (sse.jl:73-82; result, magnetization_estimator.jl:205-230) ----
         const double sign = (neg & 1u) ? -1.0 : 1.0;  // sse.jl:313
         if (lane == 0) {
