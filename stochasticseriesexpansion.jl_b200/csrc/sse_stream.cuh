@@ -146,9 +146,16 @@ struct BuildArgs {
 // Both passes read and write the ring sequentially.  vnext[] lives in the vfirst[] array: it starts as vfirst (the world
 // line is periodic: after the last operator comes the first, vertex_list.jl:46-51) and ends as vfirst again.
 
+__device__ __forceinline__ unsigned long long pack_links(uint32_t a, uint32_t b, bool fa, bool fb) {
+    return (unsigned long long)a | ((unsigned long long)b << 24) | ((unsigned long long)fa << 48) | ((unsigned long long)fb << 49);
+}
 // nearest earlier (pa/pb: its top leg) operator of the group on each of a lane's sites, and whether a later one exists
-__device__ __noinline__ void group_resolve_earlier(uint32_t inv_mask, uint32_t k0, uint32_t lane, bool nn, uint32_t sa, uint32_t sb,
-                                                   uint32_t &pa, uint32_t &pb, bool &later_a, bool &later_b) {
+// (all out-of-line helpers return their results packed in registers: a reference parameter of a __noinline__ function
+// pins the caller's variable in local memory, and the hot loops then wait on LDL/STL round trips — measured)
+__device__ __noinline__ unsigned long long group_resolve_earlier(uint32_t inv_mask, uint32_t k0, uint32_t lane, bool nn, uint32_t sa,
+                                                                 uint32_t sb) {
+    uint32_t pa = NONE24, pb = NONE24;
+    bool later_a = false, later_b = false;
     for (uint32_t mm = inv_mask; mm;) {
         const int L = __ffs(mm) - 1;
         mm &= mm - 1;
@@ -164,10 +171,13 @@ __device__ __noinline__ void group_resolve_earlier(uint32_t inv_mask, uint32_t k
             if (sb == qa || sb == qb) later_b = true;
         }
     }
+    return pack_links(pa, pb, later_a, later_b);
 }
 // nearest later (sua/sub: its bottom leg) operator of the group on each of a lane's sites, and whether an earlier one exists
-__device__ __noinline__ void group_resolve_later(uint32_t inv_mask, uint32_t k0, uint32_t lane, bool nn, uint32_t sa, uint32_t sb,
-                                                 uint32_t &sua, uint32_t &sub, bool &earlier_a, bool &earlier_b) {
+__device__ __noinline__ unsigned long long group_resolve_later(uint32_t inv_mask, uint32_t k0, uint32_t lane, bool nn, uint32_t sa,
+                                                               uint32_t sb) {
+    uint32_t sua = NONE24, sub = NONE24;
+    bool earlier_a = false, earlier_b = false;
     for (uint32_t mm = inv_mask; mm;) {
         const int L = __ffs(mm) - 1;
         mm &= mm - 1;
@@ -181,6 +191,7 @@ __device__ __noinline__ void group_resolve_later(uint32_t inv_mask, uint32_t k0,
             if (sb == qa || sb == qb) earlier_b = true;
         }
     }
+    return pack_links(sua, sub, earlier_a, earlier_b);
 }
 // operators of the group that share a site with another one: every operator tags its two sites, a lost tag reveals a
 // collision, the losers flag the contested sites, and every operator on a flagged site takes part in the search
@@ -214,7 +225,13 @@ __device__ __noinline__ void build_records(const BuildArgs b, uint32_t k0, uint3
     uint32_t pa = NONE24, pb = NONE24;
     bool later_a = false, later_b = false;
     const uint32_t inv = group_collisions(b.mark, lane, nn, sa, sb);
-    if (inv) group_resolve_earlier(inv, k0, lane, nn, sa, sb, pa, pb, later_a, later_b);
+    if (inv) {
+        const unsigned long long r = group_resolve_earlier(inv, k0, lane, nn, sa, sb);
+        pa = (uint32_t)r & NONE24;
+        pb = (uint32_t)(r >> 24) & NONE24;
+        later_a = (r >> 48) & 1ull;
+        later_b = (r >> 49) & 1ull;
+    }
     uint32_t ma = NONE32, mb = NONE32;
     if (nn) {
         if (pa == NONE24) ma = b.vlast[sa];
@@ -259,7 +276,13 @@ __device__ __noinline__ void finish_links(const BuildArgs b, uint32_t n, unsigne
         uint32_t sua = NONE24, sub = NONE24;
         bool earlier_a = false, earlier_b = false;
         const uint32_t inv = group_collisions(b.mark, lane, nn, sa, sb);
-        if (inv) group_resolve_later(inv, k0, lane, nn, sa, sb, sua, sub, earlier_a, earlier_b);
+        if (inv) {
+            const unsigned long long r = group_resolve_later(inv, k0, lane, nn, sa, sb);
+            sua = (uint32_t)r & NONE24;
+            sub = (uint32_t)(r >> 24) & NONE24;
+            earlier_a = (r >> 48) & 1ull;
+            earlier_b = (r >> 49) & 1ull;
+        }
         uint32_t na = 0, nb = 0;
         if (nn) {
             if (sua == NONE24) na = vnext[sa];
@@ -285,10 +308,9 @@ __device__ __noinline__ void finish_links(const BuildArgs b, uint32_t n, unsigne
 
 // The in-order recurrence of the accept tests (sse.jl:164-166,176-178) for a chunk in which the bound test left some lane
 // undecided: lane l only depends on lanes < l, so after i rounds the first i lanes are final (rare: ~600/(M-n) per chunk).
-__device__ __noinline__ void diag_resolve_exact(int n, int M, double p_make_bond_raw, double p_remove_bond_raw, bool is_id, bool is_dg,
-                                                double r, double w, uint32_t lt, uint32_t &ins, uint32_t &rem) {
-    ins = 0;
-    rem = 0;
+__device__ __noinline__ unsigned long long diag_resolve_exact(int n, int M, double p_make_bond_raw, double p_remove_bond_raw, bool is_id,
+                                                              bool is_dg, double r, double w, uint32_t lt) {
+    uint32_t ins = 0, rem = 0;
     while (true) {
         const int nl = n + __popc(ins & lt) - __popc(rem & lt);
         bool a2 = false;
@@ -304,20 +326,20 @@ __device__ __noinline__ void diag_resolve_exact(int n, int M, double p_make_bond
         ins = ins2;
         rem = rem2;
     }
+    return (unsigned long long)ins | ((unsigned long long)rem << 32);
 }
 
 // accept thresholds for an operator count anywhere in [lo, hi] (two divisions; recomputed every few chunks)
-__device__ __noinline__ void diag_window(int M, int lo, int hi, double p_make_bond_raw, double p_remove_bond_raw, double &pm_lo,
-                                         double &pm_hi, double &rm_sure, double &rm_maybe) {
-    pm_lo = p_make_bond_raw / (double)(M - lo);
-    pm_hi = (M - hi > 0) ? p_make_bond_raw / (double)(M - hi) : __longlong_as_double(0x7ff0000000000000ll);
-    rm_sure = (double)(M - hi + 1) * p_remove_bond_raw;
-    rm_maybe = (double)(M - lo + 1) * p_remove_bond_raw;
+__device__ __noinline__ double diag_window_make(int M, int at, double p_make_bond_raw) {
+    return (M - at > 0) ? p_make_bond_raw / (double)(M - at) : __longlong_as_double(0x7ff0000000000000ll);
 }
 
 // state seen by identity lanes / state written by off-diagonal lanes when operators of one chunk share sites (rare)
-__device__ __noinline__ void diag_resolve_state(uint32_t offm, uint32_t lane, bool is_id, bool is_off, uint32_t sa, uint32_t sb, uint32_t ta,
-                                                uint32_t tb, uint32_t &s_a, uint32_t &s_b, bool &wa, bool &wb) {
+// in/out packed: s_a | s_b << 8 | wa << 16 | wb << 17
+__device__ __noinline__ uint32_t diag_resolve_state(uint32_t offm, uint32_t lane, bool is_id, bool is_off, uint32_t sa, uint32_t sb, uint32_t ta,
+                                                    uint32_t tb, uint32_t packed) {
+    uint32_t s_a = packed & 0xffu, s_b = (packed >> 8) & 0xffu;
+    bool wa = (packed >> 16) & 1u, wb = (packed >> 17) & 1u;
     for (uint32_t m = offm; m;) {
         const int L = __ffs(m) - 1;
         m &= m - 1;
@@ -334,6 +356,7 @@ __device__ __noinline__ void diag_resolve_state(uint32_t offm, uint32_t lane, bo
             if (sb == qa || sb == qb) wb = false;
         }
     }
+    return s_a | (s_b << 8) | ((uint32_t)wa << 16) | ((uint32_t)wb << 17);
 }
 
 // one more Philox block behind the 32 a chunk's lanes computed (needed when 64 draws start at an odd stream position)
@@ -550,7 +573,14 @@ __device__ void phase_diag_build(const SmTab &st, const DevModel &dm, const DevW
                 const uint32_t anyhit = __ballot_sync(FULL, hit);
                 __syncwarp();
                 bool wa = is_off, wb = is_off;
-                if (anyhit) diag_resolve_state(offm, lane, is_id, is_off, sa, sb, ta, tb, s_a, s_b, wa, wb);
+                if (anyhit) {
+                    const uint32_t rs = diag_resolve_state(offm, lane, is_id, is_off, sa, sb, ta, tb,
+                                                           s_a | (s_b << 8) | ((uint32_t)wa << 16) | ((uint32_t)wb << 17));
+                    s_a = rs & 0xffu;
+                    s_b = (rs >> 8) & 0xffu;
+                    wa = (rs >> 16) & 1u;
+                    wb = (rs >> 17) & 1u;
+                }
                 if (is_off) {
                     if (wa) c.state[sa] = (uint8_t)ta;
                     if (wb) c.state[sb] = (uint8_t)tb;
@@ -582,7 +612,10 @@ __device__ void phase_diag_build(const SmTab &st, const DevModel &dm, const DevW
             if (n_lo < win_lo || n_hi > win_hi) {
                 win_lo = n_lo - 256;
                 win_hi = n_hi + 256;
-                diag_window(M, win_lo, win_hi, p_make_bond_raw, p_remove_bond_raw, pm_lo, pm_hi, rm_sure, rm_maybe);
+                pm_lo = diag_window_make(M, win_lo, p_make_bond_raw);
+                pm_hi = diag_window_make(M, win_hi, p_make_bond_raw);
+                rm_sure = (double)(M - win_hi + 1) * p_remove_bond_raw;
+                rm_maybe = (double)(M - win_lo + 1) * p_remove_bond_raw;
             }
             bool acc = false, amb = false;
             if (is_id) {
@@ -595,7 +628,9 @@ __device__ void phase_diag_build(const SmTab &st, const DevModel &dm, const DevW
             }
             uint32_t ins, rem;
             if (__ballot_sync(FULL, amb)) {
-                diag_resolve_exact(n, M, p_make_bond_raw, p_remove_bond_raw, is_id, is_dg, r, w, lt, ins, rem);
+                const unsigned long long ir = diag_resolve_exact(n, M, p_make_bond_raw, p_remove_bond_raw, is_id, is_dg, r, w, lt);
+                ins = (uint32_t)ir;
+                rem = (uint32_t)(ir >> 32);
             } else {
                 ins = __ballot_sync(FULL, is_id && acc);
                 rem = __ballot_sync(FULL, is_dg && acc);
