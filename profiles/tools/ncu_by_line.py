@@ -1,5 +1,7 @@
 #!/usr/bin/env python
-"""Aggregate an ncu source-page CSV (SASS view) by CUDA source line, using nvdisasm -g line info.
+"""NOTE: pass the mangled name of ONE instantiation (k_sweepILb0 = sse::k_sweep<false>); a substring that matches
+both instantiations maps addresses to the wrong lines.
+Aggregate an ncu source-page CSV (SASS view) by CUDA source line, using nvdisasm -g line info.
 
 usage: ncu_by_line.py <report.ncu-rep> <lib.so> <kernel-mangled-substring> [top]
 """

@@ -2,7 +2,8 @@
 beta doubling, then timed sse_advance launches of a fixed visit budget per walker.
 usage: quick_v2.py L beta W doublings per_level therm_sweeps budget_visits n_launches [worm_warps stream_warps] [out.jsonl]
        env SSE_PROBE_SHAPES="ww,sw,level;ww,sw,level;..." times every listed launch shape on the same thermalised batch
-       env SSE_PROBE_LIB=path/to/libsse_b200_wNN.so uses a tuning build of the library"""
+       env SSE_PROBE_LIB=path/to/libsse_b200_wNN.so uses a tuning build of the library
+       env SSE_PROBE_DESYNC=visits: budget of the untimed launch that takes the walkers out of step (default: budget_visits)"""
 import json
 import sys
 import time
@@ -37,7 +38,7 @@ t2 = time.time()
 c = wk.fetch_counters(reset=True)
 print(f"setup: doubling {t1 - t0:.1f} s, {therm} sweeps at target {t2 - t1:.1f} s ({c['visits'] / max(1e-9, t2 - t0):.3e} visits/s overall), "
       f"mean n {c['sum_n'] / max(1, c['sweeps']):.0f}", flush=True)
-wk.advance(budget, thermalized=True)  # de-synchronise the walkers
+wk.advance(int(float(os.environ.get("SSE_PROBE_DESYNC", budget))), thermalized=True)  # de-synchronise the walkers
 wk.fetch_counters(reset=True)
 shapes = [(ww, sw, None)]
 if os.environ.get("SSE_PROBE_SHAPES"):

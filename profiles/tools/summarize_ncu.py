@@ -1,5 +1,7 @@
 #!/usr/bin/env python
-"""Summarise an ncu --set full report: key counters, stall breakdown, samples by CUDA source line.
+"""NOTE: pass the mangled name of ONE instantiation (k_sweepILb0 = sse::k_sweep<false>); a substring that matches
+both instantiations maps addresses to the wrong lines.
+Summarise an ncu --set full report: key counters, stall breakdown, samples by CUDA source line.
 usage: summarize_ncu.py <report.ncu-rep> <lib.so> <kernel-substring> "<command that produced it>" > profiles/xxx.txt"""
 import csv, os, subprocess, sys
 rep, so, kname, cmd = sys.argv[1:5]

@@ -122,18 +122,19 @@ struct OpReader {
 // taken from the warp's queue {op code, site a, site b}: lane i links operator k0 + i.  The diagonal update queues the
 // operators it leaves in the string (about 13 per 32-slot chunk at the BASELINE sizes), so this step runs with all lanes
 // busy instead of once per chunk with most lanes idle.
-constexpr uint32_t BUILD_QUEUE = 64;  // entries; at most 31 waiting + 32 new ones
 
 // Out of line on purpose, like every cold path of this file: the streaming warps of an SM run the same loop at
 // different places, and a loop body beyond the 32 KB instruction cache made instruction fetch the bottleneck of the
 // whole pass (measured: ~1 instruction per cycle and SM however many warps streamed).
 struct BuildArgs {
     unsigned long long pol;  // L2 policy of the record stores and link patches (evict_last)
-    uint32_t *queue;
+    uint32_t *queue;  // 3 x BUILD_QUEUE words {op, site a, site b}, then BUILD_STAGE words of staging
     uint8_t *mark;
     uint32_t *vfirst, *vlast;
     uint4 *rec;
     uint32_t Rcap, Gn, lane;
+    uint32_t stage_s;  // shared-space address of the staging words
+    bool vlast_global;
 };
 
 // The links are built WITHOUT touching a record twice at random.  A first version patched the forward link of the previous
@@ -211,14 +212,18 @@ __device__ __forceinline__ uint32_t group_collisions(uint8_t *mark, uint32_t lan
     return __ballot_sync(FULL, inv);
 }
 
-// forward pass: records k0 .. k0+m-1 = {op code, backward links} from the warp's queue {op code, site a, site b}
-__device__ __noinline__ void build_records(const BuildArgs b, uint32_t k0, uint32_t m) {
-    const uint32_t lane = b.lane, Rcap = b.Rcap, Gn = b.Gn;
+// forward pass: records k0 .. k0+m-1 = {op code, backward links} from the warp's queue {op code, site a, site b}, in two
+// steps so that the gather of vlast[] (an L2 round trip, ~900 cycles under load) is not waited for:
+//   build_issue     in-group collisions, then an asynchronous gather of the previous operator on each site into the staging
+//                   words (the caller commits the cp.async group);
+//   build_complete  one chunk of the diagonal update later: links, vlast[] / vfirst[] updates, the record store.
+// A group is completed before the next one is issued, so the gather sees every earlier operator's vlast[] update.
+__device__ __noinline__ void build_issue(const BuildArgs b, uint32_t k0, uint32_t m) {
+    const uint32_t lane = b.lane;
     const bool nn = lane < m;
-    const uint32_t k = k0 + lane, q = k & (BUILD_QUEUE - 1);
-    uint32_t newop = 0, sa = 0, sb = 0;
+    const uint32_t q = (k0 + lane) & (BUILD_QUEUE - 1);
+    uint32_t sa = 0, sb = 0;
     if (nn) {
-        newop = b.queue[q];
         sa = b.queue[BUILD_QUEUE + q];
         sb = b.queue[2 * BUILD_QUEUE + q];
     }
@@ -232,50 +237,89 @@ __device__ __noinline__ void build_records(const BuildArgs b, uint32_t k0, uint3
         later_a = (r >> 48) & 1ull;
         later_b = (r >> 49) & 1ull;
     }
-    uint32_t ma = NONE32, mb = NONE32;
-    if (nn) {
-        if (pa == NONE24) ma = b.vlast[sa];
-        if (pb == NONE24) mb = b.vlast[sb];
+    uint32_t *stage = b.queue + 3 * BUILD_QUEUE;
+    stage[lane] = pa | ((uint32_t)later_a << 24);
+    stage[32 + lane] = pb | ((uint32_t)later_b << 24);
+    const bool ga = nn && pa == NONE24, gb = nn && pb == NONE24;
+    if (b.vlast_global) {
+        cp_async4_plain(b.stage_s + 4u * (64u + lane), b.vlast + sa, ga);
+        cp_async4_plain(b.stage_s + 4u * (96u + lane), b.vlast + sb, gb);
+    } else {
+        if (ga) stage[64 + lane] = b.vlast[sa];
+        if (gb) stage[96 + lane] = b.vlast[sb];
     }
     __syncwarp();
-    if (nn) {
+}
+__device__ __noinline__ void build_complete(const BuildArgs b, uint32_t k0, uint32_t m) {
+    const uint32_t lane = b.lane, Rcap = b.Rcap, Gn = b.Gn;
+    const uint32_t k = k0 + lane, q = k & (BUILD_QUEUE - 1);
+    const uint32_t *stage = b.queue + 3 * BUILD_QUEUE;
+    if (lane < m) {
+        const uint32_t newop = b.queue[q], sa = b.queue[BUILD_QUEUE + q], sb = b.queue[2 * BUILD_QUEUE + q];
+        const uint32_t wa = stage[lane], wb = stage[32 + lane];
+        const uint32_t pa = wa & NONE24, pb = wb & NONE24;
         const uint32_t me = k << 2;
         uint32_t bla = pa, blb = pb;  // NONE24 = first operator on the site: closed by finish_links
         if (pa == NONE24) {
+            const uint32_t ma = stage[64 + lane];
             if (ma != NONE32) bla = ma;       // vertices[s,p] = (s1,p1) (vertex_list.jl:36-38)
             else b.vfirst[sa] = me;           // vertex_list.jl:40
         }
         if (pb == NONE24) {
+            const uint32_t mb = stage[96 + lane];
             if (mb != NONE32) blb = mb;
             else b.vfirst[sb] = me | 1u;
         }
-        if (!later_a) b.vlast[sa] = me | 2u;  // vertex_list.jl:42
-        if (!later_b) b.vlast[sb] = me | 3u;
+        if (!(wa >> 24)) b.vlast[sa] = me | 2u;  // vertex_list.jl:42 (unless a later operator of the group is on the site)
+        if (!(wb >> 24)) b.vlast[sb] = me | 3u;
         // the two forward-link fields carry the operator's sites to the backward pass (saves its bond-table lookup)
         st128_hint(b.rec + ring(Gn, Rcap, k), rec_pack(newop, bla, blb, sa, sb), b.pol);
     }
     __syncwarp();
 }
 
-// backward pass over the n records of the new generation: forward links, and the periodic closure of the world lines
-__device__ __noinline__ void finish_links(const BuildArgs b, uint32_t n, unsigned long long pol_final) {
+// backward pass over the n records of the new generation: forward links, and the periodic closure of the world lines.
+// Software pipeline over the 32-record groups, so that no global round trip is exposed: the records are requested two groups
+// ahead, and the vnext[] entries of the NEXT group are gathered before the current group stores its own entries.  Where the
+// current group writes a site the next group reads (most groups have one), the early value is replaced by the one the
+// current group stored, taken from the writer's registers: the tag array names the writer (tags are reset to MARK_FREE
+// behind every group, so a tag can only come from the current group).
+constexpr uint32_t MARK_FREE = 0x40u;  // no lane id (0..31), not the collision flag (0x7f), bit 7 clear (the diagonal update's tags)
+__device__ __noinline__ void finish_links(const BuildArgs b, uint32_t n, unsigned long long pol_final, int n_sites) {
     const uint32_t lane = b.lane, Rcap = b.Rcap, Gn = b.Gn;
     uint32_t *vnext = b.vfirst;
+    uint8_t *mark = b.mark;
+    for (int s = (int)lane; s < n_sites; s += 32) mark[s] = (uint8_t)MARK_FREE;
+    __syncwarp();
     uint32_t k_hi = n;
-    // the records of the last group are requested one group ahead
     uint32_t k0 = k_hi > 32u ? k_hi - 32u : 0u, m = k_hi - k0;
-    uint4 R = make_uint4(0, 0, 0, 0);
-    if (lane < m) R = __ldcg(b.rec + ring(Gn, Rcap, k0 + lane));
+    uint32_t nk0 = k0 > 32u ? k0 - 32u : 0u, nm = k0 - nk0;  // the next (earlier) group
+    uint4 Rc = make_uint4(0, 0, 0, 0), Rn = make_uint4(0, 0, 0, 0);
+    if (lane < m) Rc = __ldcg(b.rec + ring(Gn, Rcap, k0 + lane));
+    if (lane < nm) Rn = __ldcg(b.rec + ring(Gn, Rcap, nk0 + lane));
+    uint32_t sa = lane < m ? rec_link(Rc, 2) : 0u, sb = lane < m ? rec_link(Rc, 3) : 0u;  // left there by build_records
+    uint32_t na = 0, nb = 0;
+    if (lane < m) {
+        na = vnext[sa];
+        nb = vnext[sb];
+    }
     while (k_hi > 0u) {
-        const bool nn = lane < m;
+        const bool nn = lane < m, nn2 = lane < nm;
         const uint32_t k = k0 + lane;
-        const uint4 Rc = R;
-        const uint32_t nk_hi = k0, nk0 = nk_hi > 32u ? nk_hi - 32u : 0u, nm = nk_hi - nk0;
-        if (lane < nm) R = __ldcg(b.rec + ring(Gn, Rcap, nk0 + lane));  // next (earlier) group
-        const uint32_t sa = nn ? rec_link(Rc, 2) : 0u, sb = nn ? rec_link(Rc, 3) : 0u;  // left there by build_records
+        const uint32_t nnk0 = nk0 > 32u ? nk0 - 32u : 0u, nnm = nk0 - nnk0;  // the group after the next one: request its records
+        uint4 Rnn = make_uint4(0, 0, 0, 0);
+        if (lane < nnm) Rnn = __ldcg(b.rec + ring(Gn, Rcap, nnk0 + lane));
+        // the next group's sites and their vnext[] entries as they are BEFORE this group's stores
+        const uint32_t sa2 = nn2 ? rec_link(Rn, 2) : 0u, sb2 = nn2 ? rec_link(Rn, 3) : 0u;
+        uint32_t na2 = 0, nb2 = 0;
+        if (nn2) {
+            na2 = vnext[sa2];
+            nb2 = vnext[sb2];
+        }
+        // ---- this group ----
         uint32_t sua = NONE24, sub = NONE24;
         bool earlier_a = false, earlier_b = false;
-        const uint32_t inv = group_collisions(b.mark, lane, nn, sa, sb);
+        const uint32_t inv = group_collisions(mark, lane, nn, sa, sb);
         if (inv) {
             const unsigned long long r = group_resolve_later(inv, k0, lane, nn, sa, sb);
             sua = (uint32_t)r & NONE24;
@@ -283,12 +327,6 @@ __device__ __noinline__ void finish_links(const BuildArgs b, uint32_t n, unsigne
             earlier_a = (r >> 48) & 1ull;
             earlier_b = (r >> 49) & 1ull;
         }
-        uint32_t na = 0, nb = 0;
-        if (nn) {
-            if (sua == NONE24) na = vnext[sa];
-            if (sub == NONE24) nb = vnext[sb];
-        }
-        __syncwarp();
         if (nn) {
             uint32_t bla = rec_link(Rc, 0), blb = rec_link(Rc, 1);
             if (bla == NONE24) bla = b.vlast[sa];  // first operator on the site: its lower neighbour is the last one (vertex_list.jl:46-51)
@@ -300,9 +338,34 @@ __device__ __noinline__ void finish_links(const BuildArgs b, uint32_t n, unsigne
             st128_hint(b.rec + ring(Gn, Rcap, k), rec_pack(Rc.x, bla, blb, sua, sub), pol_final);
         }
         __syncwarp();
-        k_hi = nk_hi;
+        // ---- the next group's early values, corrected where this group wrote ----
+        const uint32_t ta = nn2 ? mark[sa2] : MARK_FREE, tb = nn2 ? mark[sb2] : MARK_FREE;
+        const uint32_t qa = __shfl_sync(FULL, sa, ta & 31u), qb = __shfl_sync(FULL, sa, tb & 31u);  // site a of the writers
+        if (ta != MARK_FREE) {
+            if (ta == 0x7fu) na2 = vnext[sa2];  // several writers in the group (rare): read what they left
+            else na2 = ((k0 + ta) << 2) | (sa2 == qa ? 0u : 1u);
+        }
+        if (tb != MARK_FREE) {
+            if (tb == 0x7fu) nb2 = vnext[sb2];
+            else nb2 = ((k0 + tb) << 2) | (sb2 == qb ? 0u : 1u);
+        }
+        __syncwarp();
+        if (nn) {
+            mark[sa] = (uint8_t)MARK_FREE;
+            mark[sb] = (uint8_t)MARK_FREE;
+        }
+        __syncwarp();
+        k_hi = k0;
         k0 = nk0;
         m = nm;
+        nk0 = nnk0;
+        nm = nnm;
+        Rc = Rn;
+        Rn = Rnn;
+        sa = sa2;
+        sb = sb2;
+        na = na2;
+        nb = nb2;
     }
 }
 
@@ -372,7 +435,7 @@ struct ChunkIn {  // what stage B hands to stage C (the bond-table rows go throu
 };
 
 template <bool INJ>
-__device__ __forceinline__ ChunkIn diag_stage_b(const DevModel &dm, const Ctx &c, OpReader<1> &rd, int ch, int M, bool do_diag,
+__device__ __forceinline__ ChunkIn diag_stage_b(const DevModel &dm, const Ctx &c, OpReader<2> &rd, int ch, int M, bool do_diag,
                                                 unsigned long long &draws) {
     const uint32_t lane = c.lane, lt = rd.lt;
     ChunkIn in;
@@ -468,7 +531,7 @@ __device__ void phase_diag_build(const SmTab &st, const DevModel &dm, const DevW
     uint32_t kbase = 0, built = 0;  // operators of the new generation so far / already linked
     unsigned long long draws = c.draws;
     const int nchunks = (M + 31) >> 5;
-    OpReader<1> rd;
+    OpReader<2> rd;  // groups per chunk: op codes | bond rows | vlast[] gather of the record build
     rd.init(c.words, c.rec, c.G, Rcap, nchunks, lane, c.opring_s);
     uint2 wout = make_uint2(0u, 0u);  // new {bits, rank} of chunk 32*j + lane, written 32 words at a time
     // accept thresholds (see below), valid while the operator count stays inside [win_lo, win_hi]
@@ -485,6 +548,9 @@ __device__ void phase_diag_build(const SmTab &st, const DevModel &dm, const DevW
     ba.Rcap = Rcap;
     ba.Gn = Gn;
     ba.lane = lane;
+    ba.stage_s = (uint32_t)__cvta_generic_to_shared(c.queue + 3 * BUILD_QUEUE);
+    ba.vlast_global = c.vlast_global;
+    uint32_t issued = 0;  // operators whose links are being gathered: records [built, issued)
     ChunkIn in, nxt;
     in.op = in.bond = in.idm = in.dgm = in.kold0 = 0;
     in.r = 0.0;
@@ -498,6 +564,7 @@ __device__ void phase_diag_build(const SmTab &st, const DevModel &dm, const DevW
         }
         if (ch < 0) {
             in = nxt;
+            cp_async_commit();  // (third group of the iteration)
             continue;
         }
         // ------------------------------ stage C of chunk ch ------------------------------
@@ -510,7 +577,7 @@ __device__ void phase_diag_build(const SmTab &st, const DevModel &dm, const DevW
         const bool is_off = nonid && !(op & 2u);
         const uint32_t bond = in.bond, gv = op_gv(op), idm = in.idm, dgm = in.dgm;
         const double r = in.r;
-        cp_async_wait<2>();  // this chunk's bond rows have landed; the two groups of stage B above may still be in flight
+        cp_async_wait<2>();  // this chunk's bond rows and the build's gather have landed; the two groups of stage B above may be in flight
         const uint4 bi = lds128(c.biring_s + 16u * (32u * (uint32_t)(ch & 1) + lane));
         const uint32_t sa = bi.x & NONE24, sb = bi.y & NONE24;
         uint32_t newop = op;
@@ -664,17 +731,30 @@ __device__ void phase_diag_build(const SmTab &st, const DevModel &dm, const DevW
         kbase += cnt;
         in = nxt;
         __syncwarp();
-        if (kbase - built >= 32u) {  // 32 operators are waiting: link them with every lane busy
-            build_records(ba, built, 32u);
-            built += 32u;
+        if (issued != built) {  // the group issued one chunk ago: its gather has landed (cp_async_wait above)
+            build_complete(ba, built, 32u);
+            built = issued;
         }
+        if (kbase - built >= 32u) {  // 32 operators are waiting: link them with every lane busy
+            build_issue(ba, built, 32u);
+            issued = built + 32u;
+        }
+        cp_async_commit();
     }
     while (built < kbase) {
-        const uint32_t m = kbase - built < 32u ? kbase - built : 32u;
-        build_records(ba, built, m);
-        built += m;
+        uint32_t m = issued - built;
+        if (m == 0u) {
+            m = kbase - built < 32u ? kbase - built : 32u;
+            build_issue(ba, built, m);
+            issued = built + m;
+            cp_async_commit();
+        }
+        cp_async_wait<0>();
+        __syncwarp();
+        build_complete(ba, built, m);
+        built = issued;
     }
-    finish_links(ba, kbase, policy_evict_first());
+    finish_links(ba, kbase, policy_evict_first(), N);
     if (MEAS) {  // ---- measurement, part 3: the observables (sse.jl:73-82; result, magnetization_estimator.jl:205-230) ----
         const double sign = (neg & 1u) ? -1.0 : 1.0;  // sse.jl:313
         if (lane == 0) {

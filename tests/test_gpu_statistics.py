@@ -38,21 +38,24 @@ def test_ed_compare_gpu(job):
     assert zs.std() < 1.6, zs.std()
 
 
-@pytest.mark.parametrize("L,sweeps,replicas,seed", [(10, 3000, 24, 2026), (20, 800, 32, 2027)])
-def test_bani2v2o8_published_results_gpu(L, sweeps, replicas, seed):
+@pytest.mark.parametrize("L,sweeps,replicas,seed,therm", [(10, 3000, 24, 2026, 600), (20, 800, 32, 2027, 800)])
+def test_bani2v2o8_published_results_gpu(L, sweeps, replicas, seed, therm):
     """BASELINE config 3: S=1 honeycomb with single-ion anisotropy, all 20 temperatures range(0.05, 4, 20) of
     examples/bani2v2o8.jl:12-31 at L = 10 and L = 20 (40 published points).  Compared with the reference's published
     means within combined error bars over the whole z distribution (judge the distribution, two
     golden OperatorCount values sit ~2 sigma off a longer run).  The walkers are grown by beta doubling, so the seeds
     need no screening for the cold start's 1e8-visit worms (round 1 pre-screened them on the oracle and skipped L = 20,
     T = 0.05); 600 thermalisation sweeps at the target as in round 1 (300 left the points next to the ordering transition
-    5-8 sigma off in AbsMag/Mag2); L = 20 runs fewer sweeps on more replicas because its coldest walkers cost 0.13 s per sweep."""
+    5-8 sigma off in AbsMag/Mag2); L = 20 runs fewer sweeps on more replicas because its coldest walkers cost 0.13 s per sweep.
+    One bin per replica: the replicas are independent chains, so the jackknife error is honest even where the
+    autocorrelation time next to the ordering transition exceeds any bin length that fits inside one replica (with 100-sweep
+    bins two L = 20 temperature points had their five magnetization observables 3-4.5 sigma off together)."""
     golden = [t for t in json.load(open(GOLDEN))["tasks"] if t["L"] == L]
     assert len(golden) == 20
     model = bani_honeycomb(L)
     dm = DeviceModel(model)
     Ts = [t["T"] for t in golden]
-    res = run_gpu_tasks(dm, model, Ts, sweeps=sweeps, therm=600, binsize=100, seed=seed, replicas=replicas, doublings=3)
+    res = run_gpu_tasks(dm, model, Ts, sweeps=sweeps, therm=therm, binsize=sweeps, seed=seed, replicas=replicas, doublings=3)
     zs = {}
     for t, r in zip(golden, res):
         for name in ("Energy", "OperatorCount", "AbsMag", "Mag2", "Mag4", "MagChi", "BinderRatio", "SpecificHeat"):
@@ -64,4 +67,4 @@ def test_bani2v2o8_published_results_gpu(L, sweeps, replicas, seed):
     assert np.all(np.abs(allz) < 4.5), {k: np.round(v, 2).tolist() for k, v in zs.items()}
     assert abs(allz.mean()) < 0.6 and allz.std() < 1.6, (allz.mean(), allz.std())
     frac3 = np.mean(np.abs(allz) < 3.0)
-    assert frac3 > 0.98, frac3
+    assert frac3 > 0.98, (frac3, {k: [(round(Ts[i], 3), round(float(z), 2)) for i, z in enumerate(v) if abs(z) >= 3.0] for k, v in zs.items()})
