@@ -174,9 +174,7 @@ struct Ctx {
     uint8_t *state;              // generic pointer: shared memory or the global array
     uint8_t *mark;
     unsigned long long *rng;     // per-warp shared scratch, RNG_WORDS entries
-    uint32_t *queue;             // per-warp shared scratch: 3 x BUILD_QUEUE words, operators waiting for the record build,
-                                 // followed by 4 x 32 words of staging for the group whose links are being gathered
-    bool vlast_global;           // vlast[] lives in global memory (it can be gathered with cp.async)
+    uint32_t *queue;             // per-warp shared scratch: 3 x 64 words, operators waiting for the record build
     uint32_t opring_s, biring_s; // shared-space addresses of the warp's prefetch rings (op codes, bond-table rows)
     uint32_t *vfirst, *vlast;
     const unsigned long long *inj;
@@ -252,10 +250,6 @@ __device__ __forceinline__ void backoff(unsigned ns) { __nanosleep(ns); }
 __device__ __forceinline__ void cp_async4(uint32_t dst_s, const void *src, bool pred, unsigned long long pol) {
     const int sz = pred ? 4 : 0;
     asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 4, %2, %3;" ::"r"(dst_s), "l"(src), "r"(sz), "l"(pol) : "memory");
-}
-__device__ __forceinline__ void cp_async4_plain(uint32_t dst_s, const void *src, bool pred) {
-    const int sz = pred ? 4 : 0;
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst_s), "l"(src), "r"(sz) : "memory");
 }
 __device__ __forceinline__ void cp_async16(uint32_t dst_s, const void *src, bool pred) {
     const int sz = pred ? 16 : 0;
@@ -360,9 +354,7 @@ constexpr int OP_AHEAD = 3;              // the streaming pass requests op codes
 constexpr int OP_RING = OP_AHEAD + 1;    // chunks of op codes in flight (power of two)
 static_assert((OP_RING & (OP_RING - 1)) == 0, "OP_RING must be a power of two");
 // draws + build queue (3 x 64 words) + op-code ring (OP_RING x 32 words) + bond-row ring (2 x 32 x 16 B)
-constexpr int BUILD_QUEUE = 128;   // entries: at most 31 waiting + 32 whose links are being gathered + 32 new ones
-constexpr int BUILD_STAGE = 4 * 32;  // words: {pa|later_a, pb|later_b, vlast[sa], vlast[sb]} of the group in flight
-constexpr int STREAM_FIXED_BYTES = (((RNG_WORDS * 8) + 15) & ~15) + (3 * BUILD_QUEUE + BUILD_STAGE) * 4 + OP_RING * 32 * 4 + 2 * 32 * 16;
+constexpr int STREAM_FIXED_BYTES = (((RNG_WORDS * 8) + 15) & ~15) + 3 * 64 * 4 + OP_RING * 32 * 4 + 2 * 32 * 16;
 // bytes of shared scratch of one streaming warp: random draws + (level >= 1) state[N], mark[N] + (level 2) vlast[N]
 __host__ __device__ inline int stream_scratch_bytes(int n_sites, int level) {
     int b = STREAM_FIXED_BYTES;
@@ -378,8 +370,7 @@ __device__ __forceinline__ Ctx ctx_open(const DevModel &dm, const DevWalkers &dw
     c.lane = lane;
     c.rng = reinterpret_cast<unsigned long long *>(scratch);
     c.queue = reinterpret_cast<uint32_t *>(scratch + (((RNG_WORDS * 8) + 15) & ~15));
-    c.opring_s = (uint32_t)__cvta_generic_to_shared(c.queue + 3 * BUILD_QUEUE + BUILD_STAGE);
-    c.vlast_global = level < 2;
+    c.opring_s = (uint32_t)__cvta_generic_to_shared(c.queue + 3 * 64);
     c.biring_s = c.opring_s + OP_RING * 32 * 4;
     uint8_t *gstate = dw.state + (size_t)w * N;
     if (level) {

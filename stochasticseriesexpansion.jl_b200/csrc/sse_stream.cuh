@@ -122,19 +122,18 @@ struct OpReader {
 // taken from the warp's queue {op code, site a, site b}: lane i links operator k0 + i.  The diagonal update queues the
 // operators it leaves in the string (about 13 per 32-slot chunk at the BASELINE sizes), so this step runs with all lanes
 // busy instead of once per chunk with most lanes idle.
+constexpr uint32_t BUILD_QUEUE = 64;  // entries; at most 31 waiting + 32 new ones
 
 // Out of line on purpose, like every cold path of this file: the streaming warps of an SM run the same loop at
 // different places, and a loop body beyond the 32 KB instruction cache made instruction fetch the bottleneck of the
 // whole pass (measured: ~1 instruction per cycle and SM however many warps streamed).
 struct BuildArgs {
     unsigned long long pol;  // L2 policy of the record stores and link patches (evict_last)
-    uint32_t *queue;  // 3 x BUILD_QUEUE words {op, site a, site b}, then BUILD_STAGE words of staging
+    uint32_t *queue;
     uint8_t *mark;
     uint32_t *vfirst, *vlast;
     uint4 *rec;
     uint32_t Rcap, Gn, lane;
-    uint32_t stage_s;  // shared-space address of the staging words
-    bool vlast_global;
 };
 
 // The links are built WITHOUT touching a record twice at random.  A first version patched the forward link of the previous
@@ -212,18 +211,14 @@ __device__ __forceinline__ uint32_t group_collisions(uint8_t *mark, uint32_t lan
     return __ballot_sync(FULL, inv);
 }
 
-// forward pass: records k0 .. k0+m-1 = {op code, backward links} from the warp's queue {op code, site a, site b}, in two
-// steps so that the gather of vlast[] (an L2 round trip, ~900 cycles under load) is not waited for:
-//   build_issue     in-group collisions, then an asynchronous gather of the previous operator on each site into the staging
-//                   words (the caller commits the cp.async group);
-//   build_complete  one chunk of the diagonal update later: links, vlast[] / vfirst[] updates, the record store.
-// A group is completed before the next one is issued, so the gather sees every earlier operator's vlast[] update.
-__device__ __noinline__ void build_issue(const BuildArgs b, uint32_t k0, uint32_t m) {
-    const uint32_t lane = b.lane;
+// forward pass: records k0 .. k0+m-1 = {op code, backward links} from the warp's queue {op code, site a, site b}
+__device__ __noinline__ void build_records(const BuildArgs b, uint32_t k0, uint32_t m) {
+    const uint32_t lane = b.lane, Rcap = b.Rcap, Gn = b.Gn;
     const bool nn = lane < m;
-    const uint32_t q = (k0 + lane) & (BUILD_QUEUE - 1);
-    uint32_t sa = 0, sb = 0;
+    const uint32_t k = k0 + lane, q = k & (BUILD_QUEUE - 1);
+    uint32_t newop = 0, sa = 0, sb = 0;
     if (nn) {
+        newop = b.queue[q];
         sa = b.queue[BUILD_QUEUE + q];
         sb = b.queue[2 * BUILD_QUEUE + q];
     }
@@ -237,41 +232,25 @@ __device__ __noinline__ void build_issue(const BuildArgs b, uint32_t k0, uint32_
         later_a = (r >> 48) & 1ull;
         later_b = (r >> 49) & 1ull;
     }
-    uint32_t *stage = b.queue + 3 * BUILD_QUEUE;
-    stage[lane] = pa | ((uint32_t)later_a << 24);
-    stage[32 + lane] = pb | ((uint32_t)later_b << 24);
-    const bool ga = nn && pa == NONE24, gb = nn && pb == NONE24;
-    if (b.vlast_global) {
-        cp_async4_plain(b.stage_s + 4u * (64u + lane), b.vlast + sa, ga);
-        cp_async4_plain(b.stage_s + 4u * (96u + lane), b.vlast + sb, gb);
-    } else {
-        if (ga) stage[64 + lane] = b.vlast[sa];
-        if (gb) stage[96 + lane] = b.vlast[sb];
+    uint32_t ma = NONE32, mb = NONE32;
+    if (nn) {
+        if (pa == NONE24) ma = b.vlast[sa];
+        if (pb == NONE24) mb = b.vlast[sb];
     }
     __syncwarp();
-}
-__device__ __noinline__ void build_complete(const BuildArgs b, uint32_t k0, uint32_t m) {
-    const uint32_t lane = b.lane, Rcap = b.Rcap, Gn = b.Gn;
-    const uint32_t k = k0 + lane, q = k & (BUILD_QUEUE - 1);
-    const uint32_t *stage = b.queue + 3 * BUILD_QUEUE;
-    if (lane < m) {
-        const uint32_t newop = b.queue[q], sa = b.queue[BUILD_QUEUE + q], sb = b.queue[2 * BUILD_QUEUE + q];
-        const uint32_t wa = stage[lane], wb = stage[32 + lane];
-        const uint32_t pa = wa & NONE24, pb = wb & NONE24;
+    if (nn) {
         const uint32_t me = k << 2;
         uint32_t bla = pa, blb = pb;  // NONE24 = first operator on the site: closed by finish_links
         if (pa == NONE24) {
-            const uint32_t ma = stage[64 + lane];
             if (ma != NONE32) bla = ma;       // vertices[s,p] = (s1,p1) (vertex_list.jl:36-38)
             else b.vfirst[sa] = me;           // vertex_list.jl:40
         }
         if (pb == NONE24) {
-            const uint32_t mb = stage[96 + lane];
             if (mb != NONE32) blb = mb;
             else b.vfirst[sb] = me | 1u;
         }
-        if (!(wa >> 24)) b.vlast[sa] = me | 2u;  // vertex_list.jl:42 (unless a later operator of the group is on the site)
-        if (!(wb >> 24)) b.vlast[sb] = me | 3u;
+        if (!later_a) b.vlast[sa] = me | 2u;  // vertex_list.jl:42
+        if (!later_b) b.vlast[sb] = me | 3u;
         // the two forward-link fields carry the operator's sites to the backward pass (saves its bond-table lookup)
         st128_hint(b.rec + ring(Gn, Rcap, k), rec_pack(newop, bla, blb, sa, sb), b.pol);
     }
@@ -435,7 +414,7 @@ struct ChunkIn {  // what stage B hands to stage C (the bond-table rows go throu
 };
 
 template <bool INJ>
-__device__ __forceinline__ ChunkIn diag_stage_b(const DevModel &dm, const Ctx &c, OpReader<2> &rd, int ch, int M, bool do_diag,
+__device__ __forceinline__ ChunkIn diag_stage_b(const DevModel &dm, const Ctx &c, OpReader<1> &rd, int ch, int M, bool do_diag,
                                                 unsigned long long &draws) {
     const uint32_t lane = c.lane, lt = rd.lt;
     ChunkIn in;
@@ -531,7 +510,7 @@ __device__ void phase_diag_build(const SmTab &st, const DevModel &dm, const DevW
     uint32_t kbase = 0, built = 0;  // operators of the new generation so far / already linked
     unsigned long long draws = c.draws;
     const int nchunks = (M + 31) >> 5;
-    OpReader<2> rd;  // groups per chunk: op codes | bond rows | vlast[] gather of the record build
+    OpReader<1> rd;
     rd.init(c.words, c.rec, c.G, Rcap, nchunks, lane, c.opring_s);
     uint2 wout = make_uint2(0u, 0u);  // new {bits, rank} of chunk 32*j + lane, written 32 words at a time
     // accept thresholds (see below), valid while the operator count stays inside [win_lo, win_hi]
@@ -548,9 +527,6 @@ __device__ void phase_diag_build(const SmTab &st, const DevModel &dm, const DevW
     ba.Rcap = Rcap;
     ba.Gn = Gn;
     ba.lane = lane;
-    ba.stage_s = (uint32_t)__cvta_generic_to_shared(c.queue + 3 * BUILD_QUEUE);
-    ba.vlast_global = c.vlast_global;
-    uint32_t issued = 0;  // operators whose links are being gathered: records [built, issued)
     ChunkIn in, nxt;
     in.op = in.bond = in.idm = in.dgm = in.kold0 = 0;
     in.r = 0.0;
@@ -564,7 +540,6 @@ __device__ void phase_diag_build(const SmTab &st, const DevModel &dm, const DevW
         }
         if (ch < 0) {
             in = nxt;
-            cp_async_commit();  // (third group of the iteration)
             continue;
         }
         // ------------------------------ stage C of chunk ch ------------------------------
@@ -577,7 +552,7 @@ __device__ void phase_diag_build(const SmTab &st, const DevModel &dm, const DevW
         const bool is_off = nonid && !(op & 2u);
         const uint32_t bond = in.bond, gv = op_gv(op), idm = in.idm, dgm = in.dgm;
         const double r = in.r;
-        cp_async_wait<2>();  // this chunk's bond rows and the build's gather have landed; the two groups of stage B above may be in flight
+        cp_async_wait<2>();  // this chunk's bond rows have landed; the two groups of stage B above may still be in flight
         const uint4 bi = lds128(c.biring_s + 16u * (32u * (uint32_t)(ch & 1) + lane));
         const uint32_t sa = bi.x & NONE24, sb = bi.y & NONE24;
         uint32_t newop = op;
@@ -731,28 +706,15 @@ __device__ void phase_diag_build(const SmTab &st, const DevModel &dm, const DevW
         kbase += cnt;
         in = nxt;
         __syncwarp();
-        if (issued != built) {  // the group issued one chunk ago: its gather has landed (cp_async_wait above)
-            build_complete(ba, built, 32u);
-            built = issued;
-        }
         if (kbase - built >= 32u) {  // 32 operators are waiting: link them with every lane busy
-            build_issue(ba, built, 32u);
-            issued = built + 32u;
+            build_records(ba, built, 32u);
+            built += 32u;
         }
-        cp_async_commit();
     }
     while (built < kbase) {
-        uint32_t m = issued - built;
-        if (m == 0u) {
-            m = kbase - built < 32u ? kbase - built : 32u;
-            build_issue(ba, built, m);
-            issued = built + m;
-            cp_async_commit();
-        }
-        cp_async_wait<0>();
-        __syncwarp();
-        build_complete(ba, built, m);
-        built = issued;
+        const uint32_t m = kbase - built < 32u ? kbase - built : 32u;
+        build_records(ba, built, m);
+        built += m;
     }
     finish_links(ba, kbase, policy_evict_first(), N);
     if (MEAS) {  // ---- measurement, part 3: the observables (sse.jl:73-82; result, magnetization_estimator.jl:205-230) ----

@@ -297,7 +297,6 @@ static inline void cp_async4(uint32_t dst_s, const void *src, bool pred, unsigne
     }
     *reinterpret_cast<uint32_t *>(emu_smem_at(dst_s, 4)) = v;
 }
-static inline void cp_async4_plain(uint32_t dst_s, const void *src, bool pred) { cp_async4(dst_s, src, pred, 0ull); }
 static inline void cp_async16(uint32_t dst_s, const void *src, bool pred) {
     uint4 v = make_uint4(0, 0, 0, 0);
     if (pred) {
