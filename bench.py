@@ -187,7 +187,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(json.dumps(line))
 
 
 def setup_walkers(args, dev_index, rank, n_walkers, stream):
@@ -398,7 +398,7 @@ def run_ours(args):
                           f"{'-march=native' if native else '-march=x86-64-v3'}",
                 "per_core": r["visits"] / r["thread_seconds"],
             }
-        print(json.dumps(line))
+        emit(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -431,7 +431,32 @@ def secondary_config1(args, dev_index, stream):
             "chain_ceiling": chain_ceiling(W), "setup_s": t_setup}
 
 
+class StdoutGuard:
+    """The contract is ONE JSON line on stdout.  Libraries print there too (NCCL writes its version banner to fd 1 when
+    NCCL_DEBUG is set), so fd 1 is pointed at stderr while the benchmark runs and the line goes to the real stdout."""
+
+    def __init__(self):
+        sys.stdout.flush()
+        self.real = os.dup(1)
+        os.dup2(2, 1)
+
+    def emit(self, line):
+        sys.stdout.flush()
+        os.write(self.real, (line + "\n").encode())
+
+
+GUARD = None
+
+
+def emit(line):
+    if GUARD is not None:
+        GUARD.emit(line)
+    else:
+        print(line)
+
+
 def main():
+    global GUARD
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -471,6 +496,7 @@ def main():
         args.cpu_sweeps = max(8, int(15.0 / sweep_s))
     if args.cpu_sweeps_per_step <= 0:
         args.cpu_sweeps_per_step = max(2, int(3.0 / sweep_s))
+    GUARD = StdoutGuard()
     if args.impl == "reference":
         run_reference(args)
     else:

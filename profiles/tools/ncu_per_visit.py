@@ -28,7 +28,8 @@ out = {
     "dram_bytes_per_visit": (metric("dram__bytes_read.sum") + metric("dram__bytes_write.sum")) / visits,
     "dram_bytes_read": metric("dram__bytes_read.sum"), "dram_bytes_write": metric("dram__bytes_write.sum"),
     "warp_instructions_per_visit": metric("smsp__inst_executed.sum") / visits,
-    "duration_ms": metric("gpu__time_duration.sum") if "ms" in units[hdr.index("gpu__time_duration.sum")] else metric("gpu__time_duration.sum") * 1e-6,
+    "duration_ms": metric("gpu__time_duration.sum") * {"s": 1e3, "ms": 1.0, "us": 1e-3, "ns": 1e-6}.get(
+        units[hdr.index("gpu__time_duration.sum")].replace("second", "s").replace("msecond", "ms"), 1e-6),
     "l2_hit_rate_pct": metric("lts__t_sector_hit_rate.pct"),
     "note": "per-visit figures include the streaming phases of the sweeps the launch passes through (diagonal update, record build, "
             "measurement); algorithmic bytes per visit at this size: 64 (worm) + (12 M + 16 n)/V = 64 + 19",
