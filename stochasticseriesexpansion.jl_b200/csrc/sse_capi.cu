@@ -604,6 +604,9 @@ int32_t sse_walkers_create(const sse_model *m, const sse_walkers_opts *o, sse_wa
         ctl[i].last_wlf = NAN;
     }
     CU(cudaMemcpy(dw.ctl, ctl.data(), sizeof(WalkerCtl) * W, cudaMemcpyHostToDevice));
+    // everything above went through the legacy default stream (memsets, pageable copies that return once staged); the
+    // handle's own stream is non-blocking, so it is not ordered against them: drain before the first launch can happen
+    CU(cudaDeviceSynchronize());
     CU(cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking));
     w->own_stream = true;
     if (const char *e = getenv("SSE_B200_WORM_WARPS")) w->worm_warps = atoi(e);
