@@ -216,6 +216,9 @@ int32_t sse_get_state(sse_walkers *w, int32_t walker, sse_walker_state *st);
  * NULL buffers fills the sizes (operators_len = M) and the scalars only. */
 int32_t sse_get_states(sse_walkers *w, int32_t first, int32_t count, sse_walker_state *states);
 int32_t sse_set_state(sse_walkers *w, int32_t walker, const sse_walker_state *st);
+/* Carlo.read_checkpoint for walkers first .. first+count-1 in one round of host-to-device copies.  All states are validated
+ * against the model's tables before anything is copied: an invalid state fails the call and leaves the batch untouched. */
+int32_t sse_set_states(sse_walkers *w, int32_t first, int32_t count, const sse_walker_state *states);
 int32_t sse_get_flags(sse_walkers *w, uint32_t *flags /* [n_walkers] */);
 
 /* Carlo.parallel_tempering_log_weight_ratio / _change_parameter! (src/sse.jl:390-405), parameter :T only. */

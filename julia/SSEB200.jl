@@ -71,6 +71,18 @@ mutable struct WalkerState
     T::Float64
 end
 
+"the same layout as an isbits struct: a Vector{WalkerStateC} is a C array of sse_walker_state (sse_set_states)"
+struct WalkerStateC
+    num_operators::Int64
+    avg_worm_length::Float64
+    num_worms::Float64
+    operators::Ptr{UInt64}
+    operators_len::Int64
+    state::Ptr{UInt8}
+    rng_draws::UInt64
+    T::Float64
+end
+
 function check(status::Int32)
     status == 0 && return nothing
     error("libsse_b200: " * unsafe_string(ccall((:sse_last_error, libsse), Cstring, ())))
@@ -271,22 +283,26 @@ function Carlo.write_checkpoint(mc::MC, out::HDF5.Group)
     end
 end
 
-"Carlo.read_checkpoint (src/sse.jl:99-107) -> sse_set_state per walker.  A checkpoint written by the reference itself
-(one walker, top-level datasets, `operators` stored as OperCode structs) is accepted: the stream position defaults to 0
-and the temperature to the task's."
+"Carlo.read_checkpoint (src/sse.jl:99-107) -> one sse_set_states call for the whole batch (validated as a whole before
+anything is copied).  A checkpoint written by the reference itself (one walker, top-level datasets, `operators` stored as
+OperCode structs) is accepted: the stream position defaults to 0 and the temperature to the task's."
 function Carlo.read_checkpoint(mc::MC, in::HDF5.Group)
-    for w in eachindex(mc.T)
-        g = (length(mc.T) == 1 && !haskey(in, "walker1")) ? in : in["walker$(w)"]
+    W = length(mc.T)
+    opsv = Vector{Vector{UInt64}}(undef, W)
+    statev = Vector{Vector{UInt8}}(undef, W)
+    sts = Vector{WalkerStateC}(undef, W)
+    for w in 1:W
+        g = (W == 1 && !haskey(in, "walker1")) ? in : in["walker$(w)"]
         raw = read(g, "operators")
-        ops = eltype(raw) === UInt64 ? raw : collect(reinterpret(UInt64, raw))   # OperCode is a UInt64 wrapper (opercode.jl:33-35)
-        state = UInt8.(read(g, "state"))
+        opsv[w] = eltype(raw) === UInt64 ? raw : collect(reinterpret(UInt64, raw))   # OperCode is a UInt64 wrapper (opercode.jl:33-35)
+        statev[w] = UInt8.(read(g, "state"))
         draws = haskey(g, "rng_draws") ? read(g, "rng_draws") : UInt64(0)
         T = haskey(g, "T") ? read(g, "T") : mc.T[w]
-        GC.@preserve ops state begin
-            st = WalkerState(read(g, "num_operators"), read(g, "avg_worm_length"), read(g, "num_worms"), pointer(ops),
-                length(ops), pointer(state), draws, T)
-            check(ccall((:sse_set_state, libsse), Int32, (Ptr{Cvoid}, Int32, Ref{WalkerState}), mc.hwalkers, w - 1, st))
-        end
+        sts[w] = WalkerStateC(read(g, "num_operators"), read(g, "avg_worm_length"), read(g, "num_worms"), pointer(opsv[w]),
+            length(opsv[w]), pointer(statev[w]), draws, T)
+    end
+    GC.@preserve opsv statev begin
+        check(ccall((:sse_set_states, libsse), Int32, (Ptr{Cvoid}, Int32, Int32, Ptr{WalkerStateC}), mc.hwalkers, 0, W, sts))
     end
 end
 

@@ -152,6 +152,7 @@ def lib():
         "sse_get_state": (C.c_int32, [vp, C.c_int32, C.POINTER(WalkerState)]),
         "sse_get_states": (C.c_int32, [vp, C.c_int32, C.c_int32, C.POINTER(WalkerState)]),
         "sse_set_state": (C.c_int32, [vp, C.c_int32, C.POINTER(WalkerState)]),
+        "sse_set_states": (C.c_int32, [vp, C.c_int32, C.c_int32, C.POINTER(WalkerState)]),
         "sse_get_flags": (C.c_int32, [vp, u32p]),
         "sse_pt_log_weight_ratio": (C.c_int32, [vp, f64p, f64p]),
         "sse_set_temperature": (C.c_int32, [vp, f64p]),
@@ -189,7 +190,7 @@ EXPORTED_SYMBOLS = [
     "sse_walkers_destroy", "sse_set_stream", "sse_grow_capacity", "sse_n_observables", "sse_device_bytes", "sse_walker_bytes", "sse_init", "sse_sweep",
     "sse_sync", "sse_measure", "sse_fetch_accumulators", "sse_accumulators_device_ptr", "sse_fetch_counters",
     "sse_comm_unique_id", "sse_comm_init", "sse_reduce_bins",
-    "sse_get_state", "sse_get_states", "sse_set_state", "sse_get_flags", "sse_pt_log_weight_ratio", "sse_set_temperature",
+    "sse_get_state", "sse_get_states", "sse_set_state", "sse_set_states", "sse_get_flags", "sse_pt_log_weight_ratio", "sse_set_temperature",
     "sse_get_num_operators", "sse_get_temperatures", "sse_pt_set_ladder", "sse_pt_get_ladder", "sse_pt_exchange", "sse_pt_uniforms", "sse_double_beta", "sse_set_controller", "sse_set_launch_shape",
     "sse_advance", "sse_finish_sweeps", "sse_continue_sweeps", "sse_get_progress",
     "sse_set_injected_stream", "sse_dbg_diagonal_update", "sse_dbg_make_vertex_list",

@@ -999,37 +999,44 @@ int32_t sse_get_state(sse_walkers *w, int32_t i, sse_walker_state *st) {
     return sse_get_states(w, i, 1, st);
 }
 
-int32_t sse_set_state(sse_walkers *w, int32_t i, const sse_walker_state *st) {
-    if (!w || !st || !st->operators || !st->state) return fail("null argument");
-    if (i < 0 || i >= w->dw.W) return fail("sse_set_state: walker index out of range");
-    const sse_model *m = w->model;
-    const long long M = st->operators_len;
-    if (M < 0 || M > w->dw.M_cap) return fail("sse_set_state: operator string longer than m_capacity");
-    std::vector<uint2> words((size_t)w->dw.Mw_cap, make_uint2(0u, 0u));
+namespace {
+// host side of sse_set_state(s): the reference's UInt64 operator string -> bitmap words + records (op codes only; the links
+// are rebuilt by the next diagonal update / make_vertex_list!), validated against the model's tables
+struct StagedState {
+    std::vector<uint2> words;
     std::vector<uint4> rec;
+    WalkerCtl ctl;
+};
+int32_t stage_state(const sse_walkers *w, int32_t i, const sse_walker_state *st, StagedState &out) {
+    const sse_model *m = w->model;
+    const std::string who = "sse_set_state (walker " + std::to_string(i) + "): ";
+    if (!st->operators || !st->state) return fail(who + "null operators / state");
+    const long long M = st->operators_len;
+    if (M < 0 || M > w->dw.M_cap) return fail(who + "operator string longer than m_capacity");
+    out.words.assign((size_t)w->dw.Mw_cap, make_uint2(0u, 0u));
+    out.rec.clear();
     long long n = 0;
     for (long long p = 0; p < M; ++p) {
-        if ((p & 31) == 0) words[p >> 5].y = (uint32_t)n;
+        if ((p & 31) == 0) out.words[p >> 5].y = (uint32_t)n;
         uint64_t code = st->operators[p];
         if (code == 0) continue;
         long long bond = (long long)(code >> 26) - 1;
         uint64_t vcode = (code & ((1ull << 25) - 1)) >> 1;  // get_vertex (opercode.jl:61-62)
         long long lv = (long long)(vcode >> 1);
-        if (bond < 0 || bond >= m->dm.n_bonds) return fail("sse_set_state: bond index out of range at slot " + std::to_string(p));
+        if (bond < 0 || bond >= m->dm.n_bonds) return fail(who + "bond index out of range at slot " + std::to_string(p));
         int t = m->bond_type[bond];
         long long gv = m->type_vertex_off[t] + lv - 1;
-        if (lv < 1 || gv >= m->type_vertex_off[t + 1]) return fail("sse_set_state: vertex index out of range at slot " + std::to_string(p));
-        if ((uint32_t)(vcode & 1) != m->is_diag[gv]) return fail("sse_set_state: diagonal flag inconsistent with the vertex table at slot " + std::to_string(p));
-        words[p >> 5].x |= 1u << (p & 31);
-        rec.push_back(make_uint4(op_pack((uint32_t)bond, (uint32_t)gv, (uint32_t)(vcode & 1)), 0u, 0u, 0u));
+        if (lv < 1 || gv >= m->type_vertex_off[t + 1]) return fail(who + "vertex index out of range at slot " + std::to_string(p));
+        if ((uint32_t)(vcode & 1) != m->is_diag[gv]) return fail(who + "diagonal flag inconsistent with the vertex table at slot " + std::to_string(p));
+        out.words[p >> 5].x |= 1u << (p & 31);
+        out.rec.push_back(make_uint4(op_pack((uint32_t)bond, (uint32_t)gv, (uint32_t)(vcode & 1)), 0u, 0u, 0u));
         ++n;
     }
-    if (n != st->num_operators) return fail("sse_set_state: num_operators does not match the operator string");
-    if (n > w->dw.n_cap) return fail("sse_set_state: more operators than n_capacity");
+    if (n != st->num_operators) return fail(who + "num_operators does not match the operator string");
+    if (n > w->dw.n_cap) return fail(who + "more operators than n_capacity");
     for (int s = 0; s < m->dm.n_sites; ++s)
-        if (st->state[s] < 1 || st->state[s] > m->site_dim[s]) return fail("sse_set_state: state index out of range at site " + std::to_string(s));
-    CU(cudaStreamSynchronize(w->stream));
-    WalkerCtl c;
+        if (st->state[s] < 1 || st->state[s] > m->site_dim[s]) return fail(who + "state index out of range at site " + std::to_string(s));
+    WalkerCtl &c = out.ctl;
     memset(&c, 0, sizeof(c));
     c.T = st->T;
     c.num_worms = st->num_worms;
@@ -1038,13 +1045,37 @@ int32_t sse_set_state(sse_walkers *w, int32_t i, const sse_walker_state *st) {
     c.draws = st->rng_draws;
     c.M = (int)M;
     c.n = (int)n;
-    CU(cudaMemcpyAsync(w->dw.words + (size_t)i * w->dw.Mw_cap, words.data(), sizeof(uint2) * words.size(), cudaMemcpyHostToDevice, w->stream));
-    if (n) CU(cudaMemcpyAsync(w->dw.rec + (size_t)i * w->dw.R_cap, rec.data(), sizeof(uint4) * rec.size(), cudaMemcpyHostToDevice, w->stream));
-    CU(cudaMemcpyAsync(w->dw.state + (size_t)i * m->dm.n_sites, st->state, m->dm.n_sites, cudaMemcpyHostToDevice, w->stream));
-    CU(cudaMemcpyAsync(w->dw.ctl + i, &c, sizeof(c), cudaMemcpyHostToDevice, w->stream));
-    CU(cudaStreamSynchronize(w->stream));  // the staging vectors above are about to be freed
+    return 0;
+}
+}  // namespace
+
+int32_t sse_set_states(sse_walkers *w, int32_t first, int32_t count, const sse_walker_state *sts) {
+    if (!w || !sts) return fail("null argument");
+    if (first < 0 || count < 0 || first + count > w->dw.W) return fail("sse_set_states: walker range out of bounds");
+    if (count == 0) return 0;
+    const sse_model *m = w->model;
+    // everything is validated and staged before the first byte is copied: a bad state leaves the batch untouched
+    std::vector<StagedState> staged(count);
+    for (int j = 0; j < count; ++j)
+        if (int32_t e = stage_state(w, first + j, sts + j, staged[j])) return e;
+    CU(cudaStreamSynchronize(w->stream));
+    for (int j = 0; j < count; ++j) {
+        const int i = first + j;
+        const StagedState &g = staged[j];
+        CU(cudaMemcpyAsync(w->dw.words + (size_t)i * w->dw.Mw_cap, g.words.data(), sizeof(uint2) * g.words.size(), cudaMemcpyHostToDevice, w->stream));
+        if (!g.rec.empty()) CU(cudaMemcpyAsync(w->dw.rec + (size_t)i * w->dw.R_cap, g.rec.data(), sizeof(uint4) * g.rec.size(), cudaMemcpyHostToDevice, w->stream));
+        CU(cudaMemcpyAsync(w->dw.state + (size_t)i * m->dm.n_sites, sts[j].state, m->dm.n_sites, cudaMemcpyHostToDevice, w->stream));
+        CU(cudaMemcpyAsync(w->dw.ctl + i, &g.ctl, sizeof(WalkerCtl), cudaMemcpyHostToDevice, w->stream));
+    }
+    CU(cudaStreamSynchronize(w->stream));  // the staging vectors are about to be freed
     w->have_vl = false;
     return 0;
+}
+
+int32_t sse_set_state(sse_walkers *w, int32_t i, const sse_walker_state *st) {
+    if (!w || !st) return fail("null argument");
+    if (i < 0 || i >= w->dw.W) return fail("sse_set_state: walker index out of range");
+    return sse_set_states(w, i, 1, st);
 }
 
 int32_t sse_get_flags(sse_walkers *w, uint32_t *flags) {

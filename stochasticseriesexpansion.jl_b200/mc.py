@@ -115,8 +115,7 @@ class MC:
         return {"walkers": self.walkers.get_states()}
 
     def read_checkpoint(self, data: dict):
-        for i, s in enumerate(data["walkers"]):
-            self.walkers.set_state(i, s)
+        self.walkers.set_states(list(data["walkers"]))
 
     def parallel_tempering_log_weight_ratio(self, parameter: str, new_value):
         """sse.jl:390-396"""

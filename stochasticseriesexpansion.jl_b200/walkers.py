@@ -231,10 +231,10 @@ class Walkers:
                      operators=ops[: st.operators_len].copy(), state=state, rng_draws=int(st.rng_draws), T=float(st.T))
                 for st, (ops, state) in zip(arr, bufs)]
 
-    def set_state(self, walker: int, s: dict):
+    @staticmethod
+    def _fill_state(st, s: dict):
         ops = np.ascontiguousarray(s["operators"], dtype=np.uint64)
         state = np.ascontiguousarray(s["state"], dtype=np.uint8)
-        st = WalkerState()
         st.num_operators = int(s["num_operators"])
         st.avg_worm_length = float(s.get("avg_worm_length", 1.0))
         st.num_worms = float(s.get("num_worms", 5.0))
@@ -243,7 +243,21 @@ class Walkers:
         st.state = state.ctypes.data_as(u8p)
         st.rng_draws = int(s.get("rng_draws", 0))
         st.T = float(s["T"])
+        return ops, state  # keep the buffers alive until the call returns
+
+    def set_state(self, walker: int, s: dict):
+        st = WalkerState()
+        keep = self._fill_state(st, s)
         check(self.L.sse_set_state(self.handle, walker, C.byref(st)))
+        del keep
+
+    def set_states(self, states: list, first: int = 0):
+        """Restore walkers first .. first+len(states)-1 with one round of host-to-device copies (sse_set_states); all
+        states are validated before anything is copied."""
+        arr = (WalkerState * len(states))()
+        keep = [self._fill_state(arr[j], s) for j, s in enumerate(states)]
+        check(self.L.sse_set_states(self.handle, first, len(states), arr))
+        del keep
 
     def get_flags(self) -> np.ndarray:
         f = np.zeros(self.n_walkers, dtype=np.uint32)

@@ -234,6 +234,22 @@ def test_checkpoint_roundtrip_and_pt_hooks():
     gw2.sweep(5)
     _same_state(gw.get_state(0), gw2.get_state(0))
     _same_state(gw.get_state(1), gw2.get_state(1))
+    # the batched calls (sse_get_states / sse_set_states): one round of copies, same result
+    gw3 = Walkers(dm, [0.5, 0.7], m_capacity=4096, seed=11)
+    gw3.set_states([s0, s1])
+    gw3.sweep(5)
+    for a, b in zip(gw.get_states(), gw3.get_states()):
+        _same_state(a, b)
+    # a batch with one invalid state is rejected as a whole: walker 0 keeps what it had
+    from sse_b200.capi import SSEError
+
+    before = gw3.get_states()
+    bad = dict(s1, operators=s1["operators"].copy())
+    bad["operators"][np.flatnonzero(bad["operators"])[0]] |= np.uint64(1) << np.uint64(60)  # bond out of range
+    with pytest.raises(SSEError):
+        gw3.set_states([s0, bad])
+    for a, b in zip(before, gw3.get_states()):
+        _same_state(a, b)
     gw.set_temperature([0.9, 0.9])
     assert gw.get_state(0)["T"] == 0.9
 
