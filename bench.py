@@ -146,6 +146,20 @@ def algorithmic_bytes(sum_M, sum_n, visits, measured_sweeps=0):
     return 8.0 * sum_M + 4.0 * sum_M + 16.0 * sum_n + 64.0 * visits + 4.0 * measured_sweeps
 
 
+def host_cpu():
+    """CPU model and core count of the box (SURVEY.md 8d asks for both next to the CPU figure)."""
+    model = "unknown"
+    try:
+        with open("/proc/cpuinfo") as f:
+            for ln in f:
+                if ln.startswith("model name"):
+                    model = ln.split(":", 1)[1].strip()
+                    break
+    except OSError:
+        pass
+    return f"{model}, nproc {os.cpu_count()}"
+
+
 def cpu_baseline(args, cores=None, sweeps=None, native=True):
     """The CPU oracle (reference data layout, xoshiro256++ stream) on the host cores: one independent walker
     per thread, as Carlo runs one MC per MPI rank (docs/src/tutorial.md:49); brought to the target temperature the
@@ -183,7 +197,7 @@ def run_reference(args):
         "detail": {"note": "reference CPU path = C++ oracle restating src/sse.jl (julia is not installed in this image); "
                            "per-walker data layout of the reference", "per_core": r["visits"] / r["thread_seconds"]},
         "sweeps_per_s": r["walker_sweeps"] / r["seconds"],
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "host": host_cpu()},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -396,7 +410,7 @@ def run_ours(args):
                 "sample": f"{cores} walkers (one per host thread), thermalised like the device walkers, {sw} timed sweeps each, "
                           f"mean n={r['mean_n']:.0f}; C++ oracle, reference data layout, xoshiro256++, "
                           f"{'-march=native' if native else '-march=x86-64-v3'}",
-                "per_core": r["visits"] / r["thread_seconds"],
+                "per_core": r["visits"] / r["thread_seconds"], "host": host_cpu(),
             }
         emit(json.dumps(line))
     if world > 1:
