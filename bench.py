@@ -297,9 +297,10 @@ def run_ours(args):
         box = [Walkers.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(box, src=0)
         wk.comm_init(box[0], rank, world)
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))  # bounded so that a large --steps still fits the driver's slot
     barrier()
     t0 = time.perf_counter()
-    for k in range(args.steps):
+    for k in range(e2e_steps):
         wk.set_temperature(T_np)                                     # H2D: this step's parameters
         wk.advance(B, thermalized=True, measure=True, sync=False)    # sweeps + on-device estimators
         sums, counts = wk.reduce_bins(None, 1, reset=True)           # the bin: summed over walkers on the device, over
@@ -383,7 +384,7 @@ def run_ours(args):
                                            "what": "hops/s of W dependent 16-byte-load + 4-byte-store chains, one per lane (profiles/r2_chase_lanes.txt)"},
                          "issue_frac": issue_frac},
             "e2e": {"value": visits2 / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 8 * W,
-                    "d2h_bytes_per_step": 8 * (n_obs + 2), "ms_per_step": e2e_ms / args.steps,
+                    "d2h_bytes_per_step": 8 * (n_obs + 2), "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps,
                     "api": "sse_set_temperature + sse_advance(measure=1) + sse_reduce_bins (device sum over walkers, NCCL all-reduce "
                            "over ranks inside the library) per step",
                     "energy_per_site": energy},
@@ -494,6 +495,7 @@ def main():
     ap.add_argument("--seed", type=int, default=20261017)
     ap.add_argument("--m-capacity", type=int, default=0)
     ap.add_argument("--n-capacity", type=int, default=0)
+    ap.add_argument("--e2e-steps", type=int, default=5, help="steps of the end-to-end leg (at most --steps)")
     ap.add_argument("--carlo-steps", type=int, default=2, help="steps of the Carlo call-pattern leg (0 = skip)")
     ap.add_argument("--carlo-batch", type=int, default=4)
     ap.add_argument("--no-secondary", dest="secondary", action="store_false")
